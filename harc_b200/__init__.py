@@ -1,0 +1,246 @@
+"""harc_b200 -- ctypes binding of libharcgpu.so (include/harcgpu.h) for the tests and bench.py.
+
+The product is the C-ABI library and the two drop-in executables (`reorder.out <basedir>`, `encoder.out <basedir>`,
+the reference's process contract of harc:65-69).  This module only loads the library and mirrors its calls; it
+fails loudly when the CUDA extension is missing -- there is no CPU path.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(HERE, "libharcgpu.so")
+
+EXPORTS = [
+    "harcgpu_default_params", "harcgpu_create", "harcgpu_destroy", "harcgpu_last_error", "harcgpu_device_count",
+    "harcgpu_load_reads", "harcgpu_load_reads_device", "harcgpu_build_dicts", "harcgpu_dump_dict", "harcgpu_reorder",
+    "harcgpu_reorder_counts", "harcgpu_get_reorder", "harcgpu_get_reordered_reads", "harcgpu_get_counters",
+    "harcgpu_set_stream", "harcgpu_load_pool", "harcgpu_encode", "harcgpu_get_encode_sizes", "harcgpu_get_set_sizes",
+    "harcgpu_get_set", "harcgpu_get_globals", "harcgpu_reorder_dir", "harcgpu_encode_dir", "harcgpu_last_ms", "harcgpu_stream",
+]
+
+
+class Params(ctypes.Structure):
+    """harcgpu_params: the macros of the reference's generated src/config.h (harc:52-63) + walkers/file_sets."""
+    _fields_ = [("readlen", ctypes.c_int), ("maxmatch", ctypes.c_int), ("thresh", ctypes.c_int), ("thresh_s", ctypes.c_int),
+                ("numdict", ctypes.c_int), ("maxsearch", ctypes.c_int), ("dict_start", ctypes.c_int * 2),
+                ("dict_end", ctypes.c_int * 2), ("walkers", ctypes.c_int), ("file_sets", ctypes.c_int)]
+
+
+class EncodeSizes(ctypes.Structure):
+    _fields_ = [("n_order", ctypes.c_uint32), ("n_order_N", ctypes.c_uint32), ("singleton_bytes", ctypes.c_uint64),
+                ("singleton_tail", ctypes.c_uint64), ("input_N_bytes", ctypes.c_uint64),
+                ("aligned_singletons", ctypes.c_uint32), ("aligned_N", ctypes.c_uint32)]
+
+
+class SetSizes(ctypes.Structure):
+    _fields_ = [("seq_bytes", ctypes.c_uint64), ("seq_tail", ctypes.c_uint64), ("pos_bytes", ctypes.c_uint64),
+                ("noise_bytes", ctypes.c_uint64), ("noisepos_bytes", ctypes.c_uint64), ("rev_bytes", ctypes.c_uint64),
+                ("rev_tail", ctypes.c_uint64)]
+
+
+class Counters(ctypes.Structure):
+    _fields_ = [("steps", ctypes.c_uint64), ("probes", ctypes.c_uint64), ("key_hits", ctypes.c_uint64),
+                ("compares", ctypes.c_uint64), ("claim_fails", ctypes.c_uint64), ("restarts", ctypes.c_uint64)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load libharcgpu.so from the tree.  Raises if it has not been built: the product has no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBPATH):
+        raise RuntimeError("libharcgpu.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                           "harc_b200 has no CPU fallback")
+    lib = ctypes.CDLL(LIBPATH)
+    lib.harcgpu_last_error.restype = ctypes.c_char_p
+    lib.harcgpu_last_ms.restype = ctypes.c_double
+    lib.harcgpu_last_ms.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    lib.harcgpu_stream.restype = ctypes.c_void_p
+    lib.harcgpu_stream.argtypes = [ctypes.c_void_p]
+    lib.harcgpu_create.argtypes = [ctypes.c_int, ctypes.POINTER(Params), ctypes.POINTER(ctypes.c_void_p)]
+    lib.harcgpu_destroy.argtypes = [ctypes.c_void_p]
+    vp, u32, cp = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p
+    lib.harcgpu_load_reads.argtypes = [vp, vp, u32]
+    lib.harcgpu_load_reads_device.argtypes = [vp, vp, u32]
+    lib.harcgpu_build_dicts.argtypes = [vp]
+    lib.harcgpu_dump_dict.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]
+    lib.harcgpu_reorder.argtypes = [vp]
+    lib.harcgpu_reorder_counts.argtypes = [vp, vp, vp, vp]
+    lib.harcgpu_get_reorder.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.harcgpu_get_reordered_reads.argtypes = [vp, vp, vp]
+    lib.harcgpu_get_counters.argtypes = [vp, ctypes.POINTER(Counters)]
+    lib.harcgpu_set_stream.argtypes = [vp, vp, vp, vp, vp, vp, u32]
+    lib.harcgpu_load_pool.argtypes = [vp, vp, vp, u32, vp, u32]
+    lib.harcgpu_encode.argtypes = [vp]
+    lib.harcgpu_get_encode_sizes.argtypes = [vp, ctypes.POINTER(EncodeSizes)]
+    lib.harcgpu_get_set_sizes.argtypes = [vp, ctypes.c_int, ctypes.POINTER(SetSizes)]
+    lib.harcgpu_get_set.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
+    lib.harcgpu_get_globals.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.harcgpu_reorder_dir.argtypes = [vp, cp]
+    lib.harcgpu_encode_dir.argtypes = [vp, cp]
+    _lib = lib
+    return lib
+
+
+class HarcError(RuntimeError):
+    pass
+
+
+def default_params(readlen, walkers=0, file_sets=1):
+    lib = load_library()
+    p = Params()
+    if lib.harcgpu_default_params(int(readlen), ctypes.byref(p)):
+        raise HarcError(lib.harcgpu_last_error().decode())
+    p.walkers = walkers
+    p.file_sets = file_sets
+    return p
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, (bytes, bytearray)):
+        return ctypes.cast(ctypes.c_char_p(bytes(a)), ctypes.c_void_p)
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    assert a.flags["C_CONTIGUOUS"]
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class HarcGpu:
+    """One context on one GPU.  Method names follow include/harcgpu.h."""
+
+    def __init__(self, readlen=None, device=0, params=None, walkers=0, file_sets=1):
+        self.lib = load_library()
+        self.p = params if params is not None else default_params(readlen, walkers, file_sets)
+        self.L = self.p.readlen
+        h = ctypes.c_void_p()
+        self._ck(self.lib.harcgpu_create(device, ctypes.byref(self.p), ctypes.byref(h)))
+        self.h = h
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise HarcError(self.lib.harcgpu_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.harcgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- stage I
+    def load_reads(self, ascii_lines, n=None):
+        """ascii_lines: bytes / uint8 array holding n lines of L bases + newline (input_clean.dna)."""
+        a = np.frombuffer(ascii_lines, dtype=np.uint8) if isinstance(ascii_lines, (bytes, bytearray)) else ascii_lines
+        if n is None:
+            n = a.size // (self.L + 1)
+        self._keep = a
+        self._ck(self.lib.harcgpu_load_reads(self.h, _ptr(a), n))
+        return n
+
+    def load_reads_device(self, dptr, n):
+        self._ck(self.lib.harcgpu_load_reads_device(self.h, ctypes.c_void_p(dptr), n))
+
+    def build_dicts(self):
+        self._ck(self.lib.harcgpu_build_dicts(self.h))
+
+    def dump_dict(self, stage, l):
+        nk, ni = ctypes.c_uint32(), ctypes.c_uint32()
+        self._ck(self.lib.harcgpu_dump_dict(self.h, stage, l, None, None, None, ctypes.byref(nk), ctypes.byref(ni)))
+        keys = np.empty(nk.value, dtype=np.uint64)
+        counts = np.empty(nk.value, dtype=np.uint32)
+        ids = np.empty(ni.value, dtype=np.uint32)
+        self._ck(self.lib.harcgpu_dump_dict(self.h, stage, l, _ptr(keys), _ptr(counts), _ptr(ids), None, None))
+        return keys, counts, ids
+
+    def reorder(self):
+        self._ck(self.lib.harcgpu_reorder(self.h))
+        return self.reorder_counts()
+
+    def reorder_counts(self):
+        a, b, c = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        self._ck(self.lib.harcgpu_reorder_counts(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
+
+    def get_reorder(self):
+        m, s, _ = self.reorder_counts()
+        order = np.empty(m, dtype=np.uint32)
+        rev = np.empty(m, dtype=np.uint8)
+        flag = np.empty(m, dtype=np.uint8)
+        pos = np.empty(m, dtype=np.uint8)
+        order_s = np.empty(s, dtype=np.uint32)
+        self._ck(self.lib.harcgpu_get_reorder(self.h, _ptr(order), _ptr(rev), _ptr(flag), _ptr(pos), _ptr(order_s)))
+        return dict(order=order, rev=rev, flag=flag, pos=pos, order_s=order_s)
+
+    def get_reordered_reads(self):
+        m, s, _ = self.reorder_counts()
+        dna = np.empty(m * (self.L + 1), dtype=np.uint8)
+        sdna = np.empty(s * (self.L + 1), dtype=np.uint8)
+        self._ck(self.lib.harcgpu_get_reordered_reads(self.h, _ptr(dna), _ptr(sdna)))
+        return dna, sdna
+
+    def counters(self):
+        c = Counters()
+        self._ck(self.lib.harcgpu_get_counters(self.h, ctypes.byref(c)))
+        return {k: getattr(c, k) for k, _ in Counters._fields_}
+
+    # ---- stage II
+    def set_stream(self, dna, flag, pos, order, rev):
+        n = len(order)
+        self._keep2 = (dna, flag, pos, order, rev)
+        self._ck(self.lib.harcgpu_set_stream(self.h, _ptr(dna), _ptr(flag), _ptr(pos), _ptr(order), _ptr(rev), n))
+
+    def load_pool(self, singleton_ascii=None, order_s=None, N_ascii=None):
+        ns = 0 if order_s is None else len(order_s)
+        nN = 0 if N_ascii is None else len(N_ascii) // (self.L + 1)
+        self._keep3 = (singleton_ascii, order_s, N_ascii)
+        self._ck(self.lib.harcgpu_load_pool(self.h, _ptr(singleton_ascii), _ptr(order_s), ns, _ptr(N_ascii), nN))
+
+    def encode(self):
+        self._ck(self.lib.harcgpu_encode(self.h))
+        s = EncodeSizes()
+        self._ck(self.lib.harcgpu_get_encode_sizes(self.h, ctypes.byref(s)))
+        return s
+
+    def get_set(self, k):
+        z = SetSizes()
+        self._ck(self.lib.harcgpu_get_set_sizes(self.h, k, ctypes.byref(z)))
+        o = dict(seq=np.empty(z.seq_bytes, np.uint8), seq_tail=np.zeros(8, np.uint8), pos=np.empty(z.pos_bytes, np.uint8),
+                 noise=np.empty(z.noise_bytes, np.uint8), noisepos=np.empty(z.noisepos_bytes, np.uint8),
+                 rev=np.empty(z.rev_bytes, np.uint8), rev_tail=np.zeros(8, np.uint8))
+        self._ck(self.lib.harcgpu_get_set(self.h, k, _ptr(o["seq"]), _ptr(o["seq_tail"]), _ptr(o["pos"]), _ptr(o["noise"]),
+                                          _ptr(o["noisepos"]), _ptr(o["rev"]), _ptr(o["rev_tail"])))
+        o["seq_tail"] = o["seq_tail"][: z.seq_tail]
+        o["rev_tail"] = o["rev_tail"][: z.rev_tail]
+        return o
+
+    def get_globals(self):
+        s = EncodeSizes()
+        self._ck(self.lib.harcgpu_get_encode_sizes(self.h, ctypes.byref(s)))
+        o = dict(order=np.empty(s.n_order, np.uint32), order_N=np.empty(s.n_order_N, np.uint32),
+                 singleton=np.empty(s.singleton_bytes, np.uint8), singleton_tail=np.zeros(8, np.uint8),
+                 input_N=np.empty(s.input_N_bytes, np.uint8))
+        self._ck(self.lib.harcgpu_get_globals(self.h, _ptr(o["order"]), _ptr(o["order_N"]), _ptr(o["singleton"]),
+                                              _ptr(o["singleton_tail"]), _ptr(o["input_N"])))
+        o["singleton_tail"] = o["singleton_tail"][: s.singleton_tail]
+        return o
+
+    # ---- process contract
+    def reorder_dir(self, basedir):
+        self._ck(self.lib.harcgpu_reorder_dir(self.h, basedir.encode()))
+
+    def encode_dir(self, basedir):
+        self._ck(self.lib.harcgpu_encode_dir(self.h, basedir.encode()))
+
+    def last_ms(self, phase):
+        return self.lib.harcgpu_last_ms(self.h, phase.encode())

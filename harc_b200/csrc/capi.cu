@@ -1,0 +1,419 @@
+// C ABI of libharcgpu.so (include/harcgpu.h).  Host side only: argument checks, device memory, copies, timing.
+#include "ctx.h"
+#include <stdarg.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <string>
+#include <vector>
+
+static thread_local char g_err[1024] = "";
+void harcgpu_set_error(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof g_err, fmt, ap);
+	va_end(ap);
+}
+int s1_pack3(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *out);
+
+extern "C" {
+
+const char *harcgpu_last_error(void) { return g_err; }
+
+int harcgpu_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+// harc:52-63
+int harcgpu_default_params(int L, harcgpu_params *p)
+{
+	if (!p || L < 1 || L > 255) { harcgpu_set_error("readlen must be in 1..255"); return -1; }
+	memset(p, 0, sizeof *p);
+	p->readlen = L;
+	p->maxmatch = L / 2;
+	p->thresh = 4;
+	p->thresh_s = 24;
+	p->numdict = 2;
+	p->maxsearch = 1000;
+	p->dict_start[0] = L > 100 ? L / 2 - 32 : L / 2 - L * 32 / 100;
+	p->dict_end[0] = L / 2 - 1;
+	p->dict_start[1] = L / 2;
+	p->dict_end[1] = L > 100 ? L / 2 - 1 + 32 : L / 2 - 1 + L * 32 / 100;
+	p->walkers = 0;
+	p->file_sets = 1;
+	return 0;
+}
+
+int harcgpu_create(int device, const harcgpu_params *p, harcgpu_ctx **out)
+{
+	if (!p || !out) { harcgpu_set_error("null argument"); return -1; }
+	if (p->readlen < 1 || p->readlen > 255 || p->numdict < 1 || p->numdict > 2 || p->maxmatch < 0 || p->maxmatch > p->readlen) {
+		harcgpu_set_error("bad parameters (readlen 1..255, numdict 1..2)");
+		return -1;
+	}
+	for (int l = 0; l < p->numdict; l++)
+		if (p->dict_start[l] < 0 || p->dict_end[l] < p->dict_start[l] || p->dict_end[l] >= p->readlen ||
+		    p->dict_end[l] - p->dict_start[l] + 1 > 32) {
+			harcgpu_set_error("dictionary %d window [%d,%d] invalid (at most 32 bases inside the read)", l, p->dict_start[l], p->dict_end[l]);
+			return -1;
+		}
+	int ndev = harcgpu_device_count();
+	if (ndev <= 0) { harcgpu_set_error("no CUDA device: libharcgpu has no CPU fallback"); return -1; }
+	if (device < 0 || device >= ndev) { harcgpu_set_error("device %d out of range (%d devices)", device, ndev); return -1; }
+	CK(cudaSetDevice(device));
+	harcgpu_ctx *c = new harcgpu_ctx();
+	c->device = device;
+	c->p = *p;
+	if (c->p.file_sets <= 0) c->p.file_sets = 1;
+	c->L = p->readlen;
+	c->NW = (2 * c->L + 63) / 64;
+	c->NW3 = (3 * c->L + 63) / 64;
+	memset(&c->esz, 0, sizeof c->esz);
+	CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+	CK(cudaEventCreate(&c->ev0));
+	CK(cudaEventCreate(&c->ev1));
+	if (c->alloc(&c->counters, 8) || c->alloc(&c->gpos, 1)) return -1;
+	CK(cudaMemsetAsync(c->counters, 0, 64, c->st));
+	*out = c;
+	return 0;
+}
+
+void harcgpu_destroy(harcgpu_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->st);
+	for (void *q : c->allocs) cudaFree(q);
+	cudaEventDestroy(c->ev0);
+	cudaEventDestroy(c->ev1);
+	cudaStreamDestroy(c->st);
+	delete c;
+}
+
+void *harcgpu_stream(harcgpu_ctx *c) { return c ? (void *)c->st : nullptr; }
+
+double harcgpu_last_ms(harcgpu_ctx *c, const char *phase)
+{
+	if (!c || !phase) return -1;
+	auto it = c->ms.find(phase);
+	return it == c->ms.end() ? -1.0 : it->second;
+}
+
+static int reset_stage1(harcgpu_ctx *c, u32 n)
+{
+	c->release(c->reads); c->release(c->claim);
+	c->reads = nullptr; c->claim = nullptr;
+	for (int l = 0; l < 2; l++) free_dict(c, c->d1[l]);
+	c->dicts_built = false; c->reordered = false;
+	c->n = n;
+	if (c->alloc(&c->reads, (size_t)n * c->NW) || c->alloc(&c->claim, ((size_t)n + 31) / 32)) return -1;
+	return 0;
+}
+
+int harcgpu_load_reads_device(harcgpu_ctx *c, const void *d_ascii, u32 n)
+{
+	if (!c || (!d_ascii && n)) { harcgpu_set_error("null argument"); return -1; }
+	CK(cudaSetDevice(c->device));
+	if (reset_stage1(c, n)) return -1;
+	c->tic();
+	if (s1_pack_reads(c, d_ascii, n)) return -1;
+	c->toc("pack");
+	return 0;
+}
+
+int harcgpu_load_reads(harcgpu_ctx *c, const char *ascii, u32 n)
+{
+	if (!c || (!ascii && n)) { harcgpu_set_error("null argument"); return -1; }
+	CK(cudaSetDevice(c->device));
+	char *d = nullptr;
+	size_t bytes = (size_t)n * (c->L + 1);
+	if (c->alloc(&d, bytes + 16)) return -1;
+	CK(cudaMemcpyAsync(d, ascii, bytes, cudaMemcpyHostToDevice, c->st));
+	int rc = harcgpu_load_reads_device(c, d, n);
+	CK(cudaStreamSynchronize(c->st));
+	c->release(d);
+	return rc;
+}
+
+int harcgpu_build_dicts(harcgpu_ctx *c)
+{
+	if (!c || !c->reads) { harcgpu_set_error("load reads first"); return -1; }
+	CK(cudaSetDevice(c->device));
+	c->tic();
+	for (int l = 0; l < c->p.numdict; l++)
+		if (build_dict(c, c->d1[l], c->reads, c->n, c->NW, 2 * c->p.dict_start[l], 2 * (c->p.dict_end[l] - c->p.dict_start[l] + 1)))
+			return -1;
+	c->toc("dict");
+	c->dicts_built = true;
+	return 0;
+}
+
+int harcgpu_dump_dict(harcgpu_ctx *c, int stage, int l, uint64_t *keys, uint32_t *counts, uint32_t *ids, uint32_t *numkeys, uint32_t *nids)
+{
+	if (!c || l < 0 || l > 1 || (stage != 1 && stage != 2)) { harcgpu_set_error("bad argument"); return -1; }
+	CK(cudaSetDevice(c->device));
+	DictDev &d = stage == 1 ? c->d1[l] : c->d2[l];
+	u32 n = stage == 1 ? c->n : c->n_s + c->n_N;
+	if (!d.ids) { harcgpu_set_error("dictionary not built"); return -1; }
+	if (numkeys) *numkeys = d.numkeys;
+	if (nids) *nids = n;
+	if (keys) CK(cudaMemcpy(keys, d.keys, 8 * (size_t)d.numkeys, cudaMemcpyDeviceToHost));
+	if (ids) CK(cudaMemcpy(ids, d.ids, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+	if (counts) {
+		std::vector<u32> st((size_t)d.numkeys + 1);
+		CK(cudaMemcpy(st.data(), d.start, 4 * ((size_t)d.numkeys + 1), cudaMemcpyDeviceToHost));
+		for (u32 i = 0; i < d.numkeys; i++) counts[i] = st[i + 1] - st[i];
+	}
+	return 0;
+}
+
+int harcgpu_reorder(harcgpu_ctx *c)
+{
+	if (!c || !c->reads) { harcgpu_set_error("load reads first"); return -1; }
+	CK(cudaSetDevice(c->device));
+	if (!c->dicts_built && harcgpu_build_dicts(c)) return -1;
+	return s1_reorder(c);
+}
+
+int harcgpu_reorder_counts(harcgpu_ctx *c, uint32_t *nm, uint32_t *ns, uint32_t *nu)
+{
+	if (!c || !c->reordered) { harcgpu_set_error("reorder first"); return -1; }
+	if (nm) *nm = c->n_matched;
+	if (ns) *ns = c->n_single;
+	if (nu) *nu = c->n_unmatched;
+	return 0;
+}
+
+int harcgpu_get_reorder(harcgpu_ctx *c, uint32_t *order, char *rev, char *flag, uint8_t *pos, uint32_t *order_s)
+{
+	if (!c || !c->reordered) { harcgpu_set_error("reorder first"); return -1; }
+	CK(cudaSetDevice(c->device));
+	size_t m = c->n_matched;
+	if (order) CK(cudaMemcpyAsync(order, c->order, 4 * m, cudaMemcpyDeviceToHost, c->st));
+	if (rev) CK(cudaMemcpyAsync(rev, c->rev, m, cudaMemcpyDeviceToHost, c->st));
+	if (flag) CK(cudaMemcpyAsync(flag, c->flag, m, cudaMemcpyDeviceToHost, c->st));
+	if (pos) CK(cudaMemcpyAsync(pos, c->pos, m, cudaMemcpyDeviceToHost, c->st));
+	if (order_s) CK(cudaMemcpyAsync(order_s, c->order_s, 4 * (size_t)c->n_single, cudaMemcpyDeviceToHost, c->st));
+	CK(cudaStreamSynchronize(c->st));
+	return 0;
+}
+
+int harcgpu_get_reordered_reads(harcgpu_ctx *c, char *temp_dna, char *temp_dna_singleton)
+{
+	if (!c || !c->reordered) { harcgpu_set_error("reorder first"); return -1; }
+	CK(cudaSetDevice(c->device));
+	size_t line = (size_t)c->L + 1;
+	if (temp_dna && c->n_matched) {
+		char *d = nullptr;
+		if (c->alloc(&d, line * c->n_matched)) return -1;
+		if (s1_unpack_reads(c, c->reads, c->order, c->rev, c->n_matched, d)) return -1;
+		CK(cudaMemcpyAsync(temp_dna, d, line * c->n_matched, cudaMemcpyDeviceToHost, c->st));
+		CK(cudaStreamSynchronize(c->st));
+		c->release(d);
+	}
+	if (temp_dna_singleton && c->n_single) {
+		char *d = nullptr;
+		if (c->alloc(&d, line * c->n_single)) return -1;
+		if (s1_unpack_reads(c, c->reads, c->order_s, nullptr, c->n_single, d)) return -1;
+		CK(cudaMemcpyAsync(temp_dna_singleton, d, line * c->n_single, cudaMemcpyDeviceToHost, c->st));
+		CK(cudaStreamSynchronize(c->st));
+		c->release(d);
+	}
+	return 0;
+}
+
+int harcgpu_get_counters(harcgpu_ctx *c, harcgpu_counters *o)
+{
+	if (!c || !o) { harcgpu_set_error("null argument"); return -1; }
+	CK(cudaSetDevice(c->device));
+	u64 v[8];
+	CK(cudaMemcpy(v, c->counters, 64, cudaMemcpyDeviceToHost));
+	o->steps = v[0]; o->probes = v[1]; o->key_hits = v[2]; o->compares = v[3]; o->claim_fails = v[4]; o->restarts = v[5];
+	return 0;
+}
+
+// ---- stage II ---------------------------------------------------------------------------------------------
+int harcgpu_set_stream(harcgpu_ctx *c, const char *dna, const char *flag, const uint8_t *pos, const uint32_t *order, const char *rev, uint32_t n)
+{
+	if (!c || (n && (!dna || !flag || !pos || !order || !rev))) { harcgpu_set_error("null argument"); return -1; }
+	CK(cudaSetDevice(c->device));
+	return s2_set_stream_host(c, dna, flag, pos, order, rev, n);
+}
+
+int harcgpu_load_pool(harcgpu_ctx *c, const char *s_ascii, const uint32_t *order_s, uint32_t n_s, const char *N_ascii, uint32_t n_N)
+{
+	if (!c || (n_N && !N_ascii)) { harcgpu_set_error("null argument"); return -1; }
+	CK(cudaSetDevice(c->device));
+	return s2_load_pool(c, s_ascii, order_s, n_s, N_ascii, n_N);
+}
+
+int harcgpu_encode(harcgpu_ctx *c)
+{
+	if (!c) { harcgpu_set_error("null argument"); return -1; }
+	CK(cudaSetDevice(c->device));
+	if (!c->stream_set) {
+		if (!c->reordered) { harcgpu_set_error("no reordered stream: call harcgpu_reorder or harcgpu_set_stream first"); return -1; }
+		if (s2_set_stream_from_stage1(c)) return -1;
+	}
+	if (!c->pool_set && s2_load_pool(c, nullptr, nullptr, 0, nullptr, 0)) return -1;
+	return s2_encode(c);
+}
+
+int harcgpu_get_encode_sizes(harcgpu_ctx *c, harcgpu_encode_sizes *s)
+{
+	if (!c || !s || !c->encoded) { harcgpu_set_error("encode first"); return -1; }
+	*s = c->esz;
+	return 0;
+}
+
+int harcgpu_get_set_sizes(harcgpu_ctx *c, int k, harcgpu_set_sizes *s)
+{
+	if (!c || !s || !c->encoded || k < 0 || k >= (int)c->sets.size()) { harcgpu_set_error("bad file set"); return -1; }
+	const SetOut &o = c->sets[k];
+	s->seq_bytes = o.seq_bytes; s->seq_tail = o.seq_ntail; s->pos_bytes = o.pos_bytes; s->noise_bytes = o.noise_bytes;
+	s->noisepos_bytes = o.noisepos_bytes; s->rev_bytes = o.rev_bytes; s->rev_tail = o.rev_ntail;
+	return 0;
+}
+
+int harcgpu_get_set(harcgpu_ctx *c, int k, uint8_t *seq, char *seq_tail, uint8_t *pos, char *noise, uint8_t *noisepos, uint8_t *rev, char *rev_tail)
+{
+	if (!c || !c->encoded || k < 0 || k >= (int)c->sets.size()) { harcgpu_set_error("bad file set"); return -1; }
+	CK(cudaSetDevice(c->device));
+	const SetOut &o = c->sets[k];
+	if (seq && o.seq_bytes) CK(cudaMemcpyAsync(seq, o.seq, o.seq_bytes, cudaMemcpyDeviceToHost, c->st));
+	if (pos && o.pos_bytes) CK(cudaMemcpyAsync(pos, o.pos, o.pos_bytes, cudaMemcpyDeviceToHost, c->st));
+	if (noise && o.noise_bytes) CK(cudaMemcpyAsync(noise, o.noise, o.noise_bytes, cudaMemcpyDeviceToHost, c->st));
+	if (noisepos && o.noisepos_bytes) CK(cudaMemcpyAsync(noisepos, o.noisepos, o.noisepos_bytes, cudaMemcpyDeviceToHost, c->st));
+	if (rev && o.rev_bytes) CK(cudaMemcpyAsync(rev, o.rev, o.rev_bytes, cudaMemcpyDeviceToHost, c->st));
+	if (seq_tail) memcpy(seq_tail, o.seq_tail, o.seq_ntail);
+	if (rev_tail) memcpy(rev_tail, o.rev_tail, o.rev_ntail);
+	CK(cudaStreamSynchronize(c->st));
+	return 0;
+}
+
+int harcgpu_get_globals(harcgpu_ctx *c, uint32_t *order, uint32_t *order_N, uint8_t *singleton, char *singleton_tail, char *input_N)
+{
+	if (!c || !c->encoded) { harcgpu_set_error("encode first"); return -1; }
+	CK(cudaSetDevice(c->device));
+	if (order && c->esz.n_order) CK(cudaMemcpyAsync(order, c->o_order, 4 * (size_t)c->esz.n_order, cudaMemcpyDeviceToHost, c->st));
+	if (order_N && c->esz.n_order_N) CK(cudaMemcpyAsync(order_N, c->o_order_N, 4 * (size_t)c->esz.n_order_N, cudaMemcpyDeviceToHost, c->st));
+	if (singleton && c->esz.singleton_bytes) CK(cudaMemcpyAsync(singleton, c->o_single, c->esz.singleton_bytes, cudaMemcpyDeviceToHost, c->st));
+	if (input_N && c->esz.input_N_bytes) CK(cudaMemcpyAsync(input_N, c->o_inputN, c->esz.input_N_bytes, cudaMemcpyDeviceToHost, c->st));
+	if (singleton_tail) memcpy(singleton_tail, c->single_tail, c->esz.singleton_tail);
+	CK(cudaStreamSynchronize(c->st));
+	return 0;
+}
+
+// ---- the process contract (reorder.out / encoder.out) -------------------------------------------------------
+static bool slurp(const std::string &path, std::vector<char> &out)
+{
+	FILE *f = fopen(path.c_str(), "rb");
+	if (!f) return false;
+	struct stat sb;
+	if (fstat(fileno(f), &sb)) { fclose(f); return false; }
+	out.resize((size_t)sb.st_size);
+	size_t got = out.empty() ? 0 : fread(out.data(), 1, out.size(), f);
+	fclose(f);
+	return got == out.size();
+}
+static bool spit(const std::string &path, const void *p, size_t n)
+{
+	FILE *f = fopen(path.c_str(), "wb");
+	if (!f) return false;
+	size_t w = n ? fwrite(p, 1, n, f) : 0;
+	fclose(f);
+	return w == n;
+}
+#define FAIL(...) do { harcgpu_set_error(__VA_ARGS__); return -1; } while (0)
+
+// reorder.cpp:100-131
+int harcgpu_reorder_dir(harcgpu_ctx *c, const char *basedir)
+{
+	if (!c || !basedir) FAIL("null argument");
+	std::string out = std::string(basedir) + "/output/";
+	std::vector<char> nb, dna;
+	if (!slurp(out + "numreads.bin", nb) || nb.size() < 4) FAIL("cannot read %snumreads.bin", out.c_str());
+	u32 n;
+	memcpy(&n, nb.data(), 4);
+	if (!slurp(out + "input_clean.dna", dna) && n) FAIL("cannot read %sinput_clean.dna", out.c_str());
+	if (dna.size() < (size_t)n * (c->L + 1)) FAIL("input_clean.dna holds fewer than %u lines of %d bases", n, c->L);
+	printf("Reading file: %sinput_clean.dna\n", out.c_str());
+	if (harcgpu_load_reads(c, dna.data(), n)) return -1;
+	std::vector<char>().swap(dna);
+	if (n > 0) {
+		printf("Constructing dictionaries\n");
+		if (harcgpu_build_dicts(c)) return -1;
+	} else {
+		if (harcgpu_build_dicts(c)) return -1;
+	}
+	printf("Reordering reads\n");
+	if (harcgpu_reorder(c)) return -1;
+	printf("Reordering done, %u were unmatched\n", c->n_unmatched);
+	printf("Writing to file\n");
+	size_t m = c->n_matched, s = c->n_single, line = (size_t)c->L + 1;
+	std::vector<u32> order(m), order_s(s);
+	std::vector<char> rev(m), flag(m), tdna(m * line), sdna(s * line);
+	std::vector<u8> pos(m);
+	if (harcgpu_get_reorder(c, order.data(), rev.data(), flag.data(), pos.data(), order_s.data())) return -1;
+	if (harcgpu_get_reordered_reads(c, tdna.data(), sdna.data())) return -1;
+	if (!spit(out + "temp.dna", tdna.data(), tdna.size()) || !spit(out + "temp.dna.singleton", sdna.data(), sdna.size()) ||
+	    !spit(out + "read_rev.txt", rev.data(), m) || !spit(out + "tempflag.txt", flag.data(), m) ||
+	    !spit(out + "temppos.txt", pos.data(), m) || !spit(out + "read_order.bin", order.data(), 4 * m) ||
+	    !spit(out + "read_order.bin.singleton", order_s.data(), 4 * s))
+		FAIL("cannot write stage I files under %s", out.c_str());
+	printf("Done!\n");
+	return 0;
+}
+
+// encoder.cpp:108-152
+int harcgpu_encode_dir(harcgpu_ctx *c, const char *basedir)
+{
+	if (!c || !basedir) FAIL("null argument");
+	std::string out = std::string(basedir) + "/output/";
+	std::vector<char> order, dna, flag, pos, rc, sd, so, N;
+	size_t line = (size_t)c->L + 1;
+	if (!slurp(out + "read_order.bin", order)) FAIL("cannot read %sread_order.bin", out.c_str());
+	slurp(out + "temp.dna", dna); slurp(out + "tempflag.txt", flag); slurp(out + "temppos.txt", pos); slurp(out + "read_rev.txt", rc);
+	slurp(out + "temp.dna.singleton", sd); slurp(out + "read_order.bin.singleton", so); slurp(out + "input_N.dna", N);
+	u32 m = (u32)(order.size() / 4), ns = (u32)(sd.size() / line), nN = (u32)(N.size() / line);
+	if (dna.size() < m * line || flag.size() < m || pos.size() < m || rc.size() < m || so.size() < 4 * (size_t)ns)
+		FAIL("stage I files under %s are inconsistent", out.c_str());
+	printf("Read length: %d\nNumber of non-singleton reads: %u\nNumber of singleton reads: %u\nNumber of reads with N: %u\n", c->L, m, ns, nN);
+	if (harcgpu_set_stream(c, dna.data(), flag.data(), (const u8 *)pos.data(), (const u32 *)order.data(), rc.data(), m)) return -1;
+	if (harcgpu_load_pool(c, sd.data(), (const u32 *)so.data(), ns, N.data(), nN)) return -1;
+	printf("Encoding reads\n");
+	if (harcgpu_encode(c)) return -1;
+	harcgpu_encode_sizes es;
+	if (harcgpu_get_encode_sizes(c, &es)) return -1;
+	for (int k = 0; k < (int)c->sets.size(); k++) {
+		harcgpu_set_sizes z;
+		if (harcgpu_get_set_sizes(c, k, &z)) return -1;
+		std::vector<u8> seq(z.seq_bytes), ps(z.pos_bytes), np(z.noisepos_bytes), rv(z.rev_bytes);
+		std::vector<char> noise(z.noise_bytes);
+		char st[8], rt[8];
+		if (harcgpu_get_set(c, k, seq.data(), st, ps.data(), noise.data(), np.data(), rv.data(), rt)) return -1;
+		std::string sk = "." + std::to_string(k);
+		if (!spit(out + "read_seq.txt" + sk, seq.data(), seq.size()) || !spit(out + "read_seq.txt" + sk + ".tail", st, z.seq_tail) ||
+		    !spit(out + "read_pos.txt" + sk, ps.data(), ps.size()) || !spit(out + "read_noise.txt" + sk, noise.data(), noise.size()) ||
+		    !spit(out + "read_noisepos.txt" + sk, np.data(), np.size()) || !spit(out + "read_rev.txt" + sk, rv.data(), rv.size()) ||
+		    !spit(out + "read_rev.txt" + sk + ".tail", rt, z.rev_tail))
+			FAIL("cannot write stage II files under %s", out.c_str());
+	}
+	std::vector<u32> oo(es.n_order), oN(es.n_order_N);
+	std::vector<u8> sg(es.singleton_bytes);
+	std::vector<char> iN(es.input_N_bytes);
+	char stl[8];
+	if (harcgpu_get_globals(c, oo.data(), oN.data(), sg.data(), stl, iN.data())) return -1;
+	std::string meta = std::to_string(c->L) + "\n";
+	if (!spit(out + "read_order.bin", oo.data(), 4 * oo.size()) || !spit(out + "read_order_N_pe.bin", oN.data(), 4 * oN.size()) ||
+	    !spit(out + "read_singleton.txt", sg.data(), sg.size()) || !spit(out + "read_singleton.txt.tail", stl, es.singleton_tail) ||
+	    !spit(out + "input_N.dna", iN.data(), iN.size()) || !spit(out + "read_meta.txt", meta.data(), meta.size()))
+		FAIL("cannot write stage II files under %s", out.c_str());
+	printf("Encoding done:\n%u singleton reads were aligned\n%u reads with N were aligned\n", es.aligned_singletons, es.aligned_N);
+	return 0;
+}
+
+} // extern "C"

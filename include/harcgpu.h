@@ -1,0 +1,132 @@
+/* harcgpu.h -- C ABI of libharcgpu.so: HARC's stage I (hash-based read reordering) and stage II (consensus
+ * encoding) as sm_100a CUDA kernels.
+ *
+ * The reference has no FFI for this path: its boundary is the process + file contract `reorder.out <basedir>` /
+ * `encoder.out <basedir>` driven by harc:65-69, with the eleven macros of the generated src/config.h
+ * (harc:52-63) as parameters.  This header is what a binding for that path would bind: every entry point cites
+ * the reference code it replaces (file:line under shubhamchandak94/HARC).  The two drop-in executables
+ * (harc_b200/csrc/reorder_main.cpp, encoder_main.cpp) are thin wrappers over these calls.
+ *
+ * Conventions: every function returns 0 on success and <0 on error (harcgpu_last_error() gives the text); no
+ * exceptions cross the boundary; the caller owns every host buffer; the library owns all device memory inside the
+ * opaque context.  There is no CPU fallback: without a CUDA device every compute entry point fails.
+ * All multi-byte values are little endian, as in the reference's files.
+ */
+#ifndef HARCGPU_H
+#define HARCGPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct harcgpu_ctx harcgpu_ctx;
+
+/* The eleven macros of src/config.h (harc:52-63) as run-time values, plus the two knobs that are num_thr there. */
+typedef struct {
+	int readlen;       /* harc:62  readlen (<= 255) */
+	int maxmatch;      /* harc:52  readlen/2 */
+	int thresh;        /* harc:53  4, Hamming threshold in BITS of the 2-bit code (reorder.cpp:543) */
+	int thresh_s;      /* harc:54  24, same for the 3-bit code of stage II (encoder.cpp:296) */
+	int numdict;       /* harc:55  2 */
+	int maxsearch;     /* harc:56  1000 */
+	int dict_start[2]; /* harc:57,59 */
+	int dict_end[2];   /* harc:58,60 */
+	int walkers;       /* concurrent chain walkers = the reference's num_thr in reorder.cpp:455; 0 = choose for the GPU */
+	int file_sets;     /* K, number of read_*.txt.<k> output sets = the reference's num_thr in encoder.cpp:169-196; 0 -> 1 */
+} harcgpu_params;
+
+/* Sizes of everything stage II produced, so the caller can allocate before harcgpu_get_*.  (encoder.cpp:457-508) */
+typedef struct {
+	uint32_t n_order;        /* entries of the rewritten read_order.bin */
+	uint32_t n_order_N;      /* entries of read_order_N_pe.bin */
+	uint64_t singleton_bytes, singleton_tail; /* read_singleton.txt, read_singleton.txt.tail */
+	uint64_t input_N_bytes;  /* rewritten input_N.dna */
+	uint32_t aligned_singletons, aligned_N;   /* the two counters printed at encoder.cpp:507-508 */
+} harcgpu_encode_sizes;
+
+typedef struct {
+	uint64_t seq_bytes, seq_tail;     /* read_seq.txt.k, .tail        (encoder.cpp:519-551) */
+	uint64_t pos_bytes;               /* read_pos.txt.k               (encoder.cpp:661-663,682-683,707-708) */
+	uint64_t noise_bytes;             /* read_noise.txt.k             (encoder.cpp:673-681,698-706) */
+	uint64_t noisepos_bytes;          /* read_noisepos.txt.k */
+	uint64_t rev_bytes, rev_tail;     /* read_rev.txt.k, .tail        (encoder.cpp:554-580) */
+} harcgpu_set_sizes;
+
+/* Device-side counters of the last stage I run (SURVEY §5 "metrics"). */
+typedef struct {
+	uint64_t steps;        /* chain steps taken (= reads visited) */
+	uint64_t probes;       /* dictionary probes issued */
+	uint64_t key_hits;     /* probes whose key was present */
+	uint64_t compares;     /* candidate reads fetched and Hamming-tested */
+	uint64_t claim_fails;  /* lost CAS claims */
+	uint64_t restarts;     /* chain heads picked (= the "unmatched" count of reorder.cpp:701) */
+} harcgpu_counters;
+
+/* harc:52-63: fill p from the read length exactly as the CLI does. */
+int harcgpu_default_params(int readlen, harcgpu_params *p);
+/* One context per GPU / process.  `device` is the CUDA ordinal. */
+int harcgpu_create(int device, const harcgpu_params *p, harcgpu_ctx **out);
+void harcgpu_destroy(harcgpu_ctx *ctx);
+const char *harcgpu_last_error(void);
+int harcgpu_device_count(void);
+
+/* ---- stage I (reorder.cpp) ------------------------------------------------------------------------------ */
+/* reorder.cpp:240-263 readDnaFile + 203-209 stringtobitset.  ascii = contents of input_clean.dna: n lines of
+ * readlen chars in {A,C,G,T} + '\n' (host memory).  Copies to the device and packs 2 bits/base. */
+int harcgpu_load_reads(harcgpu_ctx *ctx, const char *ascii, uint32_t n);
+/* Same, from a buffer already resident in device memory (bench: the kernel-only figure). */
+int harcgpu_load_reads_device(harcgpu_ctx *ctx, const void *d_ascii, uint32_t n);
+/* reorder.cpp:277-394 constructdictionary (both dictionaries). */
+int harcgpu_build_dicts(harcgpu_ctx *ctx);
+/* Test hook: canonical dump (keys ascending, ids ascending inside a bin) of dictionary l of stage (1|2).
+ * With NULL buffers only *numkeys and *nids are written. */
+int harcgpu_dump_dict(harcgpu_ctx *ctx, int stage, int l, uint64_t *keys, uint32_t *counts, uint32_t *ids,
+                      uint32_t *numkeys, uint32_t *nids);
+/* reorder.cpp:434-703 reorder() incl. 863-915 updaterefcount. */
+int harcgpu_reorder(harcgpu_ctx *ctx);
+int harcgpu_reorder_counts(harcgpu_ctx *ctx, uint32_t *n_matched, uint32_t *n_singleton, uint32_t *n_unmatched);
+/* The five stage I streams: read_order.bin, read_rev.txt ('d'/'r'), tempflag.txt ('0'/'1'),
+ * temppos.txt, read_order.bin.singleton.  Any pointer may be NULL. */
+int harcgpu_get_reorder(harcgpu_ctx *ctx, uint32_t *order, char *rev, char *flag, uint8_t *pos, uint32_t *order_s);
+/* reorder.cpp:722-830 writetofile: temp.dna (n_matched lines, reverse-complemented where flagged 'r') and
+ * temp.dna.singleton (n_singleton lines).  Either pointer may be NULL. */
+int harcgpu_get_reordered_reads(harcgpu_ctx *ctx, char *temp_dna, char *temp_dna_singleton);
+int harcgpu_get_counters(harcgpu_ctx *ctx, harcgpu_counters *c);
+
+/* ---- stage II (encoder.cpp) ----------------------------------------------------------------------------- */
+/* encoder.cpp:185-225: the reordered stream as encoder.out reads it from temp.dna, tempflag.txt, temppos.txt,
+ * read_order.bin, read_rev.txt (host buffers).  Not needed after harcgpu_reorder() on the same context: the
+ * stream is then already resident on the device. */
+int harcgpu_set_stream(harcgpu_ctx *ctx, const char *temp_dna, const char *flag, const uint8_t *pos,
+                       const uint32_t *order, const char *rev, uint32_t n);
+/* encoder.cpp:823-872 readsingletons: pool = singletons ++ reads with N.  singleton_ascii/order_s may be NULL
+ * after harcgpu_reorder() on the same context (the singletons are then taken from the device). */
+int harcgpu_load_pool(harcgpu_ctx *ctx, const char *singleton_ascii, const uint32_t *order_s, uint32_t n_s,
+                      const char *N_ascii, uint32_t n_N);
+/* encoder.cpp:154-510 encode() + 512-616 packbits() + 619-717 buildcontig/writecontig. */
+int harcgpu_encode(harcgpu_ctx *ctx);
+int harcgpu_get_encode_sizes(harcgpu_ctx *ctx, harcgpu_encode_sizes *s);
+int harcgpu_get_set_sizes(harcgpu_ctx *ctx, int k, harcgpu_set_sizes *s);
+/* Copy file set k to host buffers of the sizes reported above.  Any pointer may be NULL. */
+int harcgpu_get_set(harcgpu_ctx *ctx, int k, uint8_t *seq, char *seq_tail, uint8_t *pos, char *noise,
+                    uint8_t *noisepos, uint8_t *rev, char *rev_tail);
+int harcgpu_get_globals(harcgpu_ctx *ctx, uint32_t *order, uint32_t *order_N, uint8_t *singleton,
+                        char *singleton_tail, char *input_N);
+
+/* ---- the process contract, in-process --------------------------------------------------------------------- */
+/* `reorder.out <basedir>` (reorder.cpp:100-131) and `encoder.out <basedir>` (encoder.cpp:108-152): read and write
+ * the files of SURVEY Appendix A under <basedir>/output/. */
+int harcgpu_reorder_dir(harcgpu_ctx *ctx, const char *basedir);
+int harcgpu_encode_dir(harcgpu_ctx *ctx, const char *basedir);
+
+/* Timing of the last call in milliseconds of device time (CUDA events on the context's stream): phases are
+ * "pack","dict","walk","finalize","encode".  Returns <0 for an unknown phase. */
+double harcgpu_last_ms(harcgpu_ctx *ctx, const char *phase);
+/* Raw CUDA stream of the context (cudaStream_t) so a caller can bracket calls with its own events. */
+void *harcgpu_stream(harcgpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
