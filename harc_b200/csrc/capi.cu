@@ -14,7 +14,6 @@ void harcgpu_set_error(const char *fmt, ...)
 	vsnprintf(g_err, sizeof g_err, fmt, ap);
 	va_end(ap);
 }
-int s1_pack3(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *out);
 
 extern "C" {
 
@@ -144,7 +143,7 @@ int harcgpu_build_dicts(harcgpu_ctx *c)
 	CK(cudaSetDevice(c->device));
 	c->tic();
 	for (int l = 0; l < c->p.numdict; l++)
-		if (build_dict(c, c->d1[l], c->reads, c->n, c->NW, 2 * c->p.dict_start[l], 2 * (c->p.dict_end[l] - c->p.dict_start[l] + 1)))
+		if (build_dict(c, c->d1[l], c->reads, nullptr, c->n, c->NW, c->p.dict_start[l], c->p.dict_end[l], 2))
 			return -1;
 	c->toc("dict");
 	c->dicts_built = true;

@@ -49,12 +49,14 @@ struct harcgpu_ctx {
 	u8 *s_rev = nullptr, *s_flag = nullptr, *s_pos = nullptr;
 	bool pool_set = false;
 	u32 n_s = 0, n_N = 0;   // pool = n_s singletons ++ n_N reads with N
-	u64 *pool = nullptr;    // [n_s+n_N][NW3] 3-bit packed (encoder.cpp:731-745)
+	u64 *pool = nullptr;    // [n_s+n_N][NW] 2-bit codes with N stored as 0
+	u64 *poolN = nullptr;   // [n_s+n_N][NW] bit 2i set where base i is N; 3-bit code of encoder.cpp:731-745 = 2*code2 + nflag
 	u32 *pool_order = nullptr; // order_s (encoder.cpp:865-870)
 	DictDev d2[2];
 	// ---- stage II outputs
 	bool encoded = false;
 	std::vector<SetOut> sets;
+	std::vector<void *> s2_keep; // global stage II streams the per-set views point into
 	harcgpu_encode_sizes esz;
 	u32 *o_order = nullptr, *o_order_N = nullptr;
 	u8 *o_single = nullptr; char single_tail[4];
@@ -94,7 +96,8 @@ struct harcgpu_ctx {
 
 // stage1.cu
 int s1_pack_reads(harcgpu_ctx *c, const void *d_ascii, u32 n);
-int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, u32 n, int words, int bitpos, int nbits);
+int s1_packN(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *out2, u64 *outN);
+int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, u32 n, int words, int ds, int de, int bits);
 void free_dict(harcgpu_ctx *c, DictDev &d);
 int s1_reorder(harcgpu_ctx *c);
 int s1_unpack_reads(harcgpu_ctx *c, const u64 *reads, const u32 *order, const u8 *rev, u32 cnt, char *d_out);

@@ -20,15 +20,12 @@ __device__ __forceinline__ u32 code2_of(unsigned char ch)
 	// (ch>>1)&3: A->0 C->1 T->2 G->3; reference code (reorder.cpp:188-195): A=0 G=1 C=2 T=3
 	return (0x78u >> (2 * ((ch >> 1) & 3))) & 3u;
 }
-__device__ __forceinline__ u32 code3_of(unsigned char ch)
-{
-	// encoder.cpp:731-745: N=1 (bit 3i), G=2, C=4, T=6, A=0
-	switch (ch) { case 'N': return 1; case 'G': return 2; case 'C': return 4; case 'T': return 6; default: return 0; }
-}
-
 // One block stages 64 lines in shared memory with 16-byte loads, then one thread per output word packs it.
-template <int BITS>
-__global__ void __launch_bounds__(256) pack_kernel(const char *__restrict__ ascii, u32 n, int L, int NWo, u64 *__restrict__ out)
+// WITH_N (stage II pool, encoder.cpp:731-745): 'N' is stored as code 0 and flagged in a second word array at the
+// low bit of the base's pair; the reference's 3-bit code is then 2*code2 + nflag.
+template <bool WITH_N>
+__global__ void __launch_bounds__(256) pack_kernel(const char *__restrict__ ascii, u32 n, int L, int NWo, u64 *__restrict__ out,
+                                                   u64 *__restrict__ outN)
 {
 	extern __shared__ uint4 stage4[];
 	char *stage = reinterpret_cast<char *>(stage4);
@@ -42,26 +39,20 @@ __global__ void __launch_bounds__(256) pack_kernel(const char *__restrict__ asci
 	for (size_t v = threadIdx.x; v < nvec; v += blockDim.x) stage4[v] = __ldg(&src4[v]);
 	for (size_t b = nvec * 16 + threadIdx.x; b < bytes; b += blockDim.x) stage[b] = src[b];
 	__syncthreads();
-	const int per = 64 / BITS; // bases per word when BITS==2; for BITS==3 words straddle bases, handled below
 	for (u32 w = threadIdx.x; w < nr * (u32)NWo; w += blockDim.x) {
 		u32 r = w / NWo, k = w % NWo;
 		const unsigned char *s = reinterpret_cast<const unsigned char *>(stage + (size_t)r * line);
-		u64 v = 0;
-		if (BITS == 2) {
-			int b0 = k * per;
+		u64 v = 0, vn = 0;
+		int b0 = k * 32;
 #pragma unroll 8
-			for (int c = 0; c < 32; c++)
-				if (b0 + c < L) v |= (u64)code2_of(s[b0 + c]) << (2 * c);
-		} else {
-			// word k holds bits [64k, 64k+64): bases floor(64k/3) .. floor((64k+63)/3)
-			int first = (64 * (int)k) / 3, last = min(L - 1, (64 * (int)k + 63) / 3);
-			for (int b = first; b <= last; b++) {
-				int sh = 3 * b - 64 * (int)k;
-				u64 cde = code3_of(s[b]);
-				v |= sh >= 0 ? cde << sh : cde >> (-sh);
+		for (int c = 0; c < 32; c++)
+			if (b0 + c < L) {
+				unsigned char ch = s[b0 + c];
+				if (WITH_N && ch == 'N') vn |= 1ull << (2 * c);
+				else v |= (u64)code2_of(ch) << (2 * c);
 			}
-		}
 		out[(r0 + r) * NWo + k] = v;
+		if (WITH_N) outN[(r0 + r) * NWo + k] = vn;
 	}
 }
 
@@ -102,6 +93,22 @@ __global__ void __launch_bounds__(256) keys_kernel(const u64 *__restrict__ reads
 	if (sh && q + 1 < words) v |= __ldg(&r[q + 1]) << (64 - sh);
 	if (nbits < 64) v &= (1ull << nbits) - 1;
 	keys[i] = v;
+	ids[i] = i;
+}
+
+// stage II keys (encoder.cpp:893-911): the reference's 3-bit code of base b is 2*code2 + nflag
+__global__ void __launch_bounds__(256) keys3_kernel(const u64 *__restrict__ r2, const u64 *__restrict__ rN, u32 n, int words, int ds,
+                                                    int de, u64 *__restrict__ keys, u32 *__restrict__ ids)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	u64 key = 0;
+	for (int b = ds; b <= de; b++) {
+		u64 c2 = (__ldg(&r2[(size_t)i * words + (b >> 5)]) >> (2 * (b & 31))) & 3ull;
+		u64 nf = (__ldg(&rN[(size_t)i * words + (b >> 5)]) >> (2 * (b & 31))) & 1ull;
+		key |= ((c2 << 1) | nf) << (3 * (b - ds));
+	}
+	keys[i] = key;
 	ids[i] = i;
 }
 
@@ -147,16 +154,18 @@ int s1_pack_reads(harcgpu_ctx *c, const void *d_ascii, u32 n)
 	if (n == 0) return 0;
 	size_t smem = (size_t)PACK_RPB * (c->L + 1);
 	smem = (smem + 15) / 16 * 16;
-	pack_kernel<2><<<cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, c->reads);
+	pack_kernel<false><<<cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, c->reads, nullptr);
 	CK(cudaGetLastError());
 	return 0;
 }
-int s1_pack3(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *out)
+// d_ascii must be 16-byte aligned.  out2/outN: [n][NW]
+int s1_packN(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *out2, u64 *outN)
 {
 	if (n == 0) return 0;
 	size_t smem = (size_t)PACK_RPB * (c->L + 1);
 	smem = (smem + 15) / 16 * 16;
-	pack_kernel<3><<<cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW3, out);
+	if (outN) pack_kernel<true><<<cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, out2, outN);
+	else pack_kernel<false><<<cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, out2, nullptr);
 	CK(cudaGetLastError());
 	return 0;
 }
@@ -174,10 +183,12 @@ void free_dict(harcgpu_ctx *c, DictDev &d)
 	d = DictDev();
 }
 
-int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, u32 n, int words, int bitpos, int nbits)
+// bits == 2: stage I key = bits [2*ds, 2*(de+1)) of the packed read; bits == 3: stage II key from (reads, readsN)
+int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, u32 n, int words, int ds, int de, int bits)
 {
 	cudaStream_t st = c->st;
 	free_dict(c, d);
+	const int bitpos = bits * ds, nbits = bits * (de - ds + 1);
 	d.bitpos = bitpos; d.nbits = nbits;
 	u64 *k_in = nullptr, *k_out = nullptr, *scan_tmp = nullptr;
 	u32 *id_in = nullptr, *head = nullptr, *binidx = nullptr, *d_total = nullptr;
@@ -195,7 +206,8 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, u32 n, int words, i
 	if (c->alloc(&k_in, n) || c->alloc(&k_out, n) || c->alloc(&id_in, n) || c->alloc(&head, n) || c->alloc(&binidx, n) ||
 	    c->alloc(&scan_tmp, scan_tmp_elems(n)) || c->alloc(&d_total, 1))
 		return -1;
-	keys_kernel<<<cdiv(n, 256), 256, 0, st>>>(reads, n, words, bitpos, nbits, k_in, id_in);
+	if (bits == 2) keys_kernel<<<cdiv(n, 256), 256, 0, st>>>(reads, n, words, bitpos, nbits, k_in, id_in);
+	else keys3_kernel<<<cdiv(n, 256), 256, 0, st>>>(reads, readsN, n, words, ds, de, k_in, id_in);
 	CK(cudaGetLastError());
 	size_t tb = 0;
 	CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, id_in, d.ids, (int64_t)n, 0, nbits, st));

@@ -1,6 +1,836 @@
-// placeholder, replaced below
+// Stage II of HARC -- consensus encoding (reference: src/encoder.cpp) -- as segmented sm_100a kernels.
+//
+// The reference walks the reordered stream contig by contig with std::list bookkeeping.  Here every contig is laid
+// out on ONE global column axis (contig c occupies [base_c, base_c + L + sum of its position deltas)), so that
+//   * G[i], the column where stream read i starts, is an inclusive prefix sum                   (encoder.cpp:246-251, 627-637)
+//   * the consensus of a column is a vote over the reads G[lo..hi) that cover it                 (buildcontig, 619-652)
+//   * re-aligning the pool (singletons ++ reads with N) is one probe per (column window, direction, dictionary);
+//     a pool read goes to the smallest (column, probe) that accepts it = the order in which the sequential reference
+//     would have claimed it (atomicMin on a priority word)                                       (encode, 231-418)
+//   * the final read order is a merge of two sorted lists by column                              (list inserts 254-268, 310-313)
+//   * noise / noisepos / pos / rev / order streams are scans + scatters over the merged list    (writecontig, 654-717)
+//   * packbits is a bit shuffle of the 2-bit consensus array                                     (512-616)
+// Consensus, reads and pool all live in the stage I 2-bit layout (A0 G1 C2 T3); the reference's 3-bit code is
+// 2*code2 + nflag, so its 3-bit Hamming distance is popc(x2 ^ y2) + popc(nflags).
+//
+// Known deviation (documented in DESIGN.md): a pool dictionary bin with more than maxsearch (1000) live reads is
+// scanned over its top 1000 ids only, without tracking removals; the result is still lossless.
 #include "ctx.h"
-int s2_set_stream_from_stage1(harcgpu_ctx *c) { harcgpu_set_error("stage II not built"); return -1; }
-int s2_set_stream_host(harcgpu_ctx *c, const char *, const char *, const u8 *, const u32 *, const char *, u32) { harcgpu_set_error("stage II not built"); return -1; }
-int s2_load_pool(harcgpu_ctx *c, const char *, const u32 *, u32, const char *, u32) { harcgpu_set_error("stage II not built"); return -1; }
-int s2_encode(harcgpu_ctx *c) { harcgpu_set_error("stage II not built"); return -1; }
+#include <cub/device/device_radix_sort.cuh>
+
+namespace {
+constexpr u32 CAP1 = 10000001u; // encoder.cpp:226: a contig is cut once list_size > 10000000
+constexpr u64 NOBEST = ~0ull;
+
+__device__ __forceinline__ u64 revpairs64(u64 x)
+{
+	u64 y = __brevll(x);
+	return ((y & 0x5555555555555555ull) << 1) | ((y >> 1) & 0x5555555555555555ull);
+}
+__device__ __forceinline__ u64 swappairs64(u64 x) // bit code (A0 G1 C2 T3) <-> file code (A0 C1 G2 T3)
+{
+	return ((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull);
+}
+// reverse the base order of an L-base sequence (2 bits/base) held in NW words; no complement
+template <int NW>
+__device__ __forceinline__ void reverse2(const u64 (&in)[NW], int L, u64 (&out)[NW])
+{
+	u64 t[NW + 1];
+#pragma unroll
+	for (int k = 0; k < NW; k++) t[k] = revpairs64(in[NW - 1 - k]);
+	t[NW] = 0;
+	const int s = 2 * (32 * NW - L);
+#pragma unroll
+	for (int k = 0; k < NW; k++) out[k] = s ? (t[k] >> s) | (t[k + 1] << (64 - s)) : t[k];
+}
+template <int NW>
+__device__ __forceinline__ void load_words(const u64 *__restrict__ p, u64 (&w)[NW])
+{
+#pragma unroll
+	for (int k = 0; k < NW; k++) w[k] = __ldg(&p[k]);
+}
+// reverse complement of a pool read (N stays N): r2 = codes, rn = N flags
+template <int NW>
+__device__ __forceinline__ void revcomp_pool(u64 (&r2)[NW], u64 (&rn)[NW], int L)
+{
+	u64 a[NW], b[NW];
+	reverse2<NW>(r2, L, a);
+	reverse2<NW>(rn, L, b);
+#pragma unroll
+	for (int k = 0; k < NW; k++) {
+		u64 valid = lowmask(2 * L - 64 * k);
+		r2[k] = (a[k] ^ valid) & ~(b[k] | (b[k] << 1));
+		rn[k] = b[k];
+	}
+}
+// bits [2g, 2g+2L) of the consensus bit array (two zero pad words follow the array)
+template <int NW>
+__device__ __forceinline__ void load_window(const u64 *__restrict__ cons2, u64 g, int L, u64 (&w)[NW])
+{
+	const u64 bit = 2 * g;
+	const size_t q = (size_t)(bit >> 6);
+	const int r = (int)(bit & 63);
+#pragma unroll
+	for (int k = 0; k < NW; k++) {
+		u64 lo = __ldg(&cons2[q + k]), hi = __ldg(&cons2[q + k + 1]);
+		w[k] = (r ? (lo >> r) | (hi << (64 - r)) : lo) & lowmask(2 * L - 64 * k);
+	}
+}
+__device__ __forceinline__ u64 getbits_g(const u64 *__restrict__ w, u64 bit, int n)
+{
+	const size_t q = (size_t)(bit >> 6);
+	const int r = (int)(bit & 63);
+	u64 v = __ldg(&w[q]) >> r;
+	if (r) v |= __ldg(&w[q + 1]) << (64 - r);
+	if (n < 64) v &= (1ull << n) - 1;
+	return v;
+}
+// first index in [0,n) with a[i] > v
+__device__ __forceinline__ u32 upper_bound64(const u64 *__restrict__ a, u32 n, u64 v)
+{
+	u64 lo = 0, hi = n;
+	while (lo < hi) {
+		u64 mid = (lo + hi) >> 1;
+		if (__ldg(&a[mid]) <= v) lo = mid + 1; else hi = mid;
+	}
+	return (u32)lo;
+}
+
+// ---------------------------------------------------------------------------------------------- contig layout
+__global__ void __launch_bounds__(256) natstart_kernel(const u8 *__restrict__ flag, u32 m, u32 per, u32 *__restrict__ ns)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m) return;
+	ns[i] = (flag[i] == '0' || i % per == 0) ? 1u : 0u; // flag '0' or first read of a thread range (encoder.cpp:226, 169-180)
+}
+__global__ void __launch_bounds__(256) scatter_idx_kernel(const u32 *__restrict__ f, const u32 *__restrict__ ex, u32 m, u32 *__restrict__ out)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < m && f[i]) out[ex[i]] = i;
+}
+__global__ void __launch_bounds__(256) cstart_kernel(const u32 *__restrict__ ns, const u32 *__restrict__ ex_ns, const u32 *__restrict__ nat_idx,
+                                                     const u8 *__restrict__ pos, u32 m, int L, u32 *__restrict__ cs, u64 *__restrict__ inc)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m) return;
+	u32 c = ex_ns[i] + ns[i] - 1;
+	u32 idx = i - nat_idx[c];
+	u32 s = (idx % CAP1 == 0) ? 1u : 0u;
+	cs[i] = s;
+	inc[i] = s ? (i ? (u64)L : 0ull) : (u64)pos[i];
+}
+__global__ void __launch_bounds__(256) finish_layout_kernel(const u32 *__restrict__ cs, const u32 *__restrict__ ex_cs, const u64 *__restrict__ inc,
+                                                            u64 *__restrict__ G, u32 m, u32 *__restrict__ cid, u32 *__restrict__ cstart)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m) return;
+	G[i] += inc[i]; // exclusive -> inclusive
+	u32 c = ex_cs[i] + cs[i] - 1;
+	cid[i] = c;
+	if (cs[i]) cstart[c] = i;
+}
+
+// ---------------------------------------------------------------------------------------------- consensus
+// One lane per column, one warp per 32 columns = one u64 of the packed consensus (encoder.cpp:619-652).
+__global__ void __launch_bounds__(256) consensus_kernel(const u64 *__restrict__ G, const u64 *__restrict__ sreads, u32 m, int L, int NW,
+                                                        u64 TOT, u64 *__restrict__ cons2)
+{
+	const u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (w * 32 >= TOT) return;
+	const u64 g = w * 32 + lane;
+	u32 code = 0;
+	if (g < TOT) {
+		u32 hi = upper_bound64(G, m, g);
+		u32 lo = g >= (u64)L ? upper_bound64(G, m, g - L) : 0u;
+		u32 cA = 0, cC = 0, cG = 0, cT = 0;
+		for (u32 i = lo; i < hi; i++) {
+			u32 o = (u32)(g - __ldg(&G[i]));
+			u32 v = (u32)(__ldg(&sreads[(size_t)i * NW + (o >> 5)]) >> (2 * (o & 31))) & 3u;
+			cA += v == 0; cG += v == 1; cC += v == 2; cT += v == 3;
+		}
+		// ties -> A < C < G < T, strict '>' from max = 0 (encoder.cpp:642-648)
+		u32 mx = 0;
+		if (cA > mx) { mx = cA; code = 0; }
+		if (cC > mx) { mx = cC; code = 2; }
+		if (cG > mx) { mx = cG; code = 1; }
+		if (cT > mx) { mx = cT; code = 3; }
+	}
+	u32 b0 = __ballot_sync(0xffffffffu, code & 1u), b1 = __ballot_sync(0xffffffffu, (code >> 1) & 1u);
+	if (lane == 0) {
+		u64 lo = b0, hi = b1, v = 0;
+		// interleave
+		lo = (lo | (lo << 16)) & 0x0000FFFF0000FFFFull; lo = (lo | (lo << 8)) & 0x00FF00FF00FF00FFull;
+		lo = (lo | (lo << 4)) & 0x0F0F0F0F0F0F0F0Full; lo = (lo | (lo << 2)) & 0x3333333333333333ull;
+		lo = (lo | (lo << 1)) & 0x5555555555555555ull;
+		hi = (hi | (hi << 16)) & 0x0000FFFF0000FFFFull; hi = (hi | (hi << 8)) & 0x00FF00FF00FF00FFull;
+		hi = (hi | (hi << 4)) & 0x0F0F0F0F0F0F0F0Full; hi = (hi | (hi << 2)) & 0x3333333333333333ull;
+		hi = (hi | (hi << 1)) & 0x5555555555555555ull;
+		v = lo | (hi << 1);
+		cons2[w] = v;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------- pool re-alignment
+struct PoolArgs {
+	const u64 *G; const u32 *cid; const u32 *cstart;
+	u32 m, NC, per;
+	u64 TOT;
+	const u64 *cons2;
+	const u64 *pool, *poolN;
+	DictView d[2];
+	int L, thresh_s, maxsearch;
+	u64 *best;
+};
+
+__device__ __forceinline__ u64 spread2to3(u64 k2, int nb) // base t: 2-bit code c -> 3-bit code 2c at bits 3t
+{
+	u64 k3 = 0;
+	for (int t = 0; t < nb; t++) k3 |= (((k2 >> (2 * t)) & 3ull) << 1) << (3 * t);
+	return k3;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(128) pool_probe_kernel(PoolArgs a)
+{
+	const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	const int L = a.L;
+	if (a.TOT < (u64)L || g > a.TOT - L) return;
+	// which contig does column g belong to, and may a window start here?
+	u32 r = upper_bound64(a.G, a.m, g) - 1;
+	u32 c = __ldg(&a.cid[r]);
+	u32 next = c + 1 < a.NC ? __ldg(&a.cstart[c + 1]) : a.m;
+	if (next == a.m || next % a.per == 0) return; // last contig of its thread range: written without alignment (encoder.cpp:438-441)
+	if (g + L > __ldg(&a.G[next])) return;        // j <= ref.size()-readlen (encoder.cpp:252)
+	u64 w[NW], rc[NW];
+	bool have_w = false, have_rc = false;
+	for (int q = 0; q < 4; q++) { // forward dict 0, forward dict 1, reverse dict 0, reverse dict 1 (encoder.cpp:270, 338)
+		const int l = q & 1;
+		const bool rev = q >= 2;
+		const DictView &dv = a.d[l];
+		const int nb = dv.dend - dv.dstart + 1;
+		u64 k2;
+		if (!rev) k2 = getbits_g(a.cons2, 2 * (g + dv.dstart), 2 * nb);
+		else {
+			k2 = getbits_g(a.cons2, 2 * (g + L - 1 - dv.dend), 2 * nb);
+			k2 = revpairs64(~k2 & lowmask(2 * nb)) >> (64 - 2 * nb);
+		}
+		u32 bstart, bsize;
+		if (!dict_lookup(dv, spread2to3(k2, nb), bstart, bsize)) continue;
+		if (!have_w) { load_window<NW>(a.cons2, g, L, w); have_w = true; }
+		if (rev && !have_rc) {
+			u64 t[NW];
+			reverse2<NW>(w, L, t);
+#pragma unroll
+			for (int k = 0; k < NW; k++) rc[k] = t[k] ^ lowmask(2 * L - 64 * k);
+			have_rc = true;
+		}
+		long long end = (long long)bstart + bsize, lo = max((long long)bstart, end - a.maxsearch);
+		for (long long t = end - 1; t >= lo; t--) { // no break: every read of the bin within thresh_s is taken (293-317)
+			u32 rid = __ldg(&dv.ids[t]);
+			const u64 *p2 = a.pool + (size_t)rid * NW, *pn = a.poolN + (size_t)rid * NW;
+			int d = 0;
+#pragma unroll
+			for (int k = 0; k < NW; k++) d += __popcll((rev ? rc[k] : w[k]) ^ __ldg(&p2[k])) + __popcll(__ldg(&pn[k]));
+			if (d <= a.thresh_s) atomicMin(&a.best[rid], (g << 2) | (u64)q);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) fill64_kernel(u64 *p, size_t n, u64 v)
+{
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) p[i] = v;
+}
+// aligned pool reads in DESCENDING id order (the bin scan order, encoder.cpp:293), then stably sorted by priority
+__global__ void __launch_bounds__(256) aligned_flag_kernel(const u64 *__restrict__ best, u32 P, u32 *__restrict__ af)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < P) af[i] = best[P - 1 - i] != NOBEST;
+}
+__global__ void __launch_bounds__(256) aligned_compact_kernel(const u64 *__restrict__ best, const u32 *__restrict__ af, const u32 *__restrict__ ex,
+                                                              u32 P, u64 *__restrict__ prio, u32 *__restrict__ rid)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P || !af[i]) return;
+	prio[ex[i]] = best[P - 1 - i];
+	rid[ex[i]] = P - 1 - i;
+}
+
+// ---------------------------------------------------------------------------------------------- merge
+__global__ void __launch_bounds__(256) place_orig_kernel(const u64 *__restrict__ G, u32 m, const u64 *__restrict__ iprio, u32 M,
+                                                         u32 *__restrict__ f_src, u8 *__restrict__ f_kind, u64 *__restrict__ f_col)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m) return;
+	u64 g = G[i];
+	u64 lo = 0, hi = M; // inserted reads with column < g come first; at equal column the original comes first (254-268)
+	while (lo < hi) {
+		u64 mid = (lo + hi) >> 1;
+		if ((__ldg(&iprio[mid]) >> 2) < g) lo = mid + 1; else hi = mid;
+	}
+	size_t e = (size_t)i + lo;
+	f_src[e] = i; f_kind[e] = 0; f_col[e] = g;
+}
+__global__ void __launch_bounds__(256) place_ins_kernel(const u64 *__restrict__ G, u32 m, const u64 *__restrict__ iprio, const u32 *__restrict__ irid,
+                                                        u32 M, u32 *__restrict__ f_src, u8 *__restrict__ f_kind, u64 *__restrict__ f_col)
+{
+	u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= M) return;
+	u64 pr = iprio[k], col = pr >> 2;
+	size_t e = (size_t)k + upper_bound64(G, m, col);
+	f_src[e] = irid[k]; f_kind[e] = (u8)(1u | (((pr & 3ull) >= 2) ? 2u : 0u)); f_col[e] = col;
+}
+
+// ---------------------------------------------------------------------------------------------- emission
+struct EmitArgs {
+	const u32 *f_src; const u8 *f_kind; const u64 *f_col; u64 F;
+	const u64 *sreads; const u32 *cs; const u32 *s_order; const u8 *s_rev;
+	const u64 *pool, *poolN; const u32 *pool_order; u32 n_s;
+	const u64 *cons2;
+	int L;
+	// pass 1 outputs
+	u64 *nm1; u8 *posb; u8 *revc; u32 *isN; u32 *ordv;
+	// pass 2 inputs / outputs
+	const u64 *noff; const u32 *exN;
+	char *noise; u8 *noisepos; u32 *o_order; u32 *o_order_N;
+};
+
+template <int NW>
+__device__ __forceinline__ void entry_mismatches(const EmitArgs &a, u64 e, u64 (&rw)[NW], u64 (&rn)[NW], u64 (&cw)[NW], u64 (&mm)[NW])
+{
+	const u32 src = a.f_src[e];
+	const u8 kind = a.f_kind[e];
+	if (kind == 0) {
+		load_words<NW>(a.sreads + (size_t)src * NW, rw);
+#pragma unroll
+		for (int k = 0; k < NW; k++) rn[k] = 0;
+	} else {
+		load_words<NW>(a.pool + (size_t)src * NW, rw);
+		load_words<NW>(a.poolN + (size_t)src * NW, rn);
+		if (kind & 2) revcomp_pool<NW>(rw, rn, a.L); // stored as reverse_complement(read) (encoder.cpp:375)
+	}
+	load_window<NW>(a.cons2, a.f_col[e], a.L, cw);
+#pragma unroll
+	for (int k = 0; k < NW; k++) {
+		u64 x = rw[k] ^ cw[k];
+		mm[k] = ((x | (x >> 1)) & 0x5555555555555555ull) | rn[k];
+	}
+}
+
+template <int NW>
+__global__ void __launch_bounds__(128) emit_count_kernel(EmitArgs a)
+{
+	const u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= a.F) return;
+	u64 rw[NW], rn[NW], cw[NW], mm[NW];
+	entry_mismatches<NW>(a, e, rw, rn, cw, mm);
+	int nm = 0;
+#pragma unroll
+	for (int k = 0; k < NW; k++) nm += __popcll(mm[k]);
+	a.nm1[e] = (u64)nm + 1;
+	const u32 src = a.f_src[e];
+	const u8 kind = a.f_kind[e];
+	// first read of a contig: readlen; otherwise delta to the previous read of the merged list (661-663, 682-683, 707-708)
+	a.posb[e] = (kind == 0 && a.cs[src]) ? (u8)a.L : (u8)(a.f_col[e] - a.f_col[e - 1]);
+	a.revc[e] = kind == 0 ? a.s_rev[src] : ((kind & 2) ? 'r' : 'd');
+	a.isN[e] = (kind != 0 && src >= a.n_s) ? 1u : 0u; // only reads from input_N.dna contain 'N' (684-687)
+	a.ordv[e] = kind == 0 ? a.s_order[src] : a.pool_order[src];
+}
+
+// enc_noise[ref][read] (encoder.cpp:752-771), indexed by the 2-bit code A0 G1 C2 T3 and N=4
+__device__ __constant__ char kNoise[4][5] = {
+	{ 0, '1', '0', '2', '3' }, // ref A: C0 G1 T2 N3
+	{ '1', 0, '2', '0', '3' }, // ref G: T0 A1 C2 N3
+	{ '0', '1', 0, '2', '3' }, // ref C: A0 G1 T2 N3
+	{ '2', '0', '1', 0, '3' }, // ref T: G0 C1 A2 N3
+};
+
+template <int NW>
+__global__ void __launch_bounds__(128) emit_write_kernel(EmitArgs a)
+{
+	const u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= a.F) return;
+	u64 rw[NW], rn[NW], cw[NW], mm[NW];
+	entry_mismatches<NW>(a, e, rw, rn, cw, mm);
+	const u64 no = a.noff[e];
+	char *np = a.noise + no;
+	u8 *pp = a.noisepos + (no - e);
+	int t = 0, prev = 0;
+#pragma unroll
+	for (int k = 0; k < NW; k++) {
+		u64 mk = mm[k];
+		while (mk) {
+			int b = __ffsll((long long)mk) - 1;
+			mk &= mk - 1;
+			int p = 32 * k + (b >> 1);
+			u32 rf = (u32)(cw[k] >> b) & 3u;
+			u32 rd = ((rn[k] >> b) & 1ull) ? 4u : ((u32)(rw[k] >> b) & 3u);
+			np[t] = kNoise[rf][rd];
+			pp[t] = (u8)(p - prev); // delta from the previous noise position of this read, first one absolute (677-679)
+			prev = p;
+			t++;
+		}
+	}
+	np[t] = '\n';
+	if (a.isN[e]) a.o_order_N[a.exN[e]] = a.ordv[e];
+	else a.o_order[e - a.exN[e]] = a.ordv[e];
+}
+
+// ---------------------------------------------------------------------------------------------- packbits (512-616)
+// seq: 4 bases per byte, base k of a group at bits 2k, A0 C1 G2 T3
+__global__ void __launch_bounds__(256) pack_seq_kernel(const u64 *__restrict__ cons2, u64 col0, u64 nbytes, u8 *__restrict__ out)
+{
+	u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nbytes) return;
+	out[b] = (u8)swappairs64(getbits_g(cons2, 2 * (col0 + 4 * b), 8));
+}
+// rev: 8 flags per byte, LSB first, d=0 r=1
+__global__ void __launch_bounds__(256) pack_rev_kernel(const u8 *__restrict__ revc, u64 e0, u64 nbytes, u8 *__restrict__ out)
+{
+	u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nbytes) return;
+	u32 v = 0;
+#pragma unroll
+	for (int k = 0; k < 8; k++) v |= (revc[e0 + 8 * b + k] == 'r' ? 1u : 0u) << k;
+	out[b] = (u8)v;
+}
+// the <4 leftover bases / <8 leftover flags go to the .tail files as ASCII
+__global__ void tails_kernel(const u64 *__restrict__ cons2, u64 colend, u32 nseq, const u8 *__restrict__ revc, u64 eend, u32 nrev, char *__restrict__ out)
+{
+	if (threadIdx.x < nseq) out[threadIdx.x] = "AGCT"[getbits_g(cons2, 2 * (colend - nseq + threadIdx.x), 2)];
+	if (threadIdx.x < nrev) out[4 + threadIdx.x] = (char)revc[eend - nrev + threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------- unaligned pool reads (476-499)
+__global__ void __launch_bounds__(256) unaligned_flag_kernel(const u64 *__restrict__ best, u32 P, u32 *__restrict__ uf)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < P) uf[i] = best[i] == NOBEST;
+}
+__global__ void __launch_bounds__(256) unaligned_kernel(const u32 *__restrict__ uf, const u32 *__restrict__ exU, u32 P, u32 n_s, u32 U_s,
+                                                        const u32 *__restrict__ pool_order, u32 *__restrict__ ulist,
+                                                        u32 *__restrict__ o_order_tail, u32 *__restrict__ o_order_N_tail)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P || !uf[i]) return;
+	u32 u = exU[i];
+	ulist[u] = i;
+	if (i < n_s) o_order_tail[u] = pool_order[i];
+	else o_order_N_tail[u - U_s] = pool_order[i];
+}
+__global__ void __launch_bounds__(256) pack_singleton_kernel(const u64 *__restrict__ pool, const u32 *__restrict__ ulist, int L, int NW,
+                                                             u64 nbases, u64 nbytes, u8 *__restrict__ out, char *__restrict__ tail)
+{
+	u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (b > nbytes) return;
+	u32 v = 0;
+	for (int k = 0; k < 4; k++) {
+		u64 t = 4 * b + k;
+		if (t >= nbases) break;
+		u32 rid = ulist[t / L];
+		int off = (int)(t % L);
+		u32 c = (u32)(__ldg(&pool[(size_t)rid * NW + (off >> 5)]) >> (2 * (off & 31))) & 3u;
+		if (b == nbytes) tail[k] = "AGCT"[c];
+		v |= (((c & 1u) << 1) | (c >> 1)) << (2 * k);
+	}
+	if (b < nbytes) out[b] = (u8)v;
+}
+__global__ void __launch_bounds__(256) unaligned_N_kernel(const u64 *__restrict__ pool, const u64 *__restrict__ poolN, const u32 *__restrict__ ulist,
+                                                          int L, int NW, u64 nbytes, char *__restrict__ out)
+{
+	u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nbytes) return;
+	u64 line = b / (L + 1);
+	int c = (int)(b % (L + 1));
+	char ch = '\n';
+	if (c < L) {
+		u32 rid = ulist[line];
+		u64 w2 = __ldg(&pool[(size_t)rid * NW + (c >> 5)]), wn = __ldg(&poolN[(size_t)rid * NW + (c >> 5)]);
+		ch = ((wn >> (2 * (c & 31))) & 1ull) ? 'N' : "AGCT"[(w2 >> (2 * (c & 31))) & 3ull];
+	}
+	out[b] = ch;
+}
+
+// ---------------------------------------------------------------------------------------------- hand-off from stage I
+template <int NW>
+__global__ void __launch_bounds__(128) gather_stream_kernel(const u64 *__restrict__ reads, const u32 *__restrict__ order, const u8 *__restrict__ rev,
+                                                            u32 cnt, int L, u64 *__restrict__ out)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= cnt) return;
+	u64 r[NW];
+	load_words<NW>(reads + (size_t)order[i] * NW, r);
+	if (rev && rev[i] == 'r') { // temp.dna holds the read already reverse-complemented (reorder.cpp:744-752)
+		u64 t[NW];
+		reverse2<NW>(r, L, t);
+#pragma unroll
+		for (int k = 0; k < NW; k++) r[k] = t[k] ^ lowmask(2 * L - 64 * k);
+	}
+#pragma unroll
+	for (int k = 0; k < NW; k++) out[(size_t)i * NW + k] = r[k];
+}
+__global__ void __launch_bounds__(256) iota_off_kernel(u32 *v, u32 n)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) v[i] = i;
+}
+} // namespace
+
+#define DISPATCH_NW(NWv, CALL)                                                                    \
+	switch (NWv) {                                                                                \
+	case 1: { constexpr int NW = 1; CALL; } break;                                                \
+	case 2: { constexpr int NW = 2; CALL; } break;                                                \
+	case 3: { constexpr int NW = 3; CALL; } break;                                                \
+	case 4: { constexpr int NW = 4; CALL; } break;                                                \
+	case 5: { constexpr int NW = 5; CALL; } break;                                                \
+	case 6: { constexpr int NW = 6; CALL; } break;                                                \
+	case 7: { constexpr int NW = 7; CALL; } break;                                                \
+	case 8: { constexpr int NW = 8; CALL; } break;                                                \
+	default: harcgpu_set_error("unsupported read length"); return -1;                              \
+	}
+
+static void free_stream(harcgpu_ctx *c)
+{
+	c->release(c->sreads); c->release(c->s_order); c->release(c->s_rev); c->release(c->s_flag); c->release(c->s_pos);
+	c->sreads = nullptr; c->s_order = nullptr; c->s_rev = c->s_flag = c->s_pos = nullptr;
+	c->stream_set = false; c->encoded = false;
+}
+static void free_pool(harcgpu_ctx *c)
+{
+	c->release(c->pool); c->release(c->poolN); c->release(c->pool_order);
+	c->pool = c->poolN = nullptr; c->pool_order = nullptr;
+	for (int l = 0; l < 2; l++) free_dict(c, c->d2[l]);
+	c->pool_set = false; c->encoded = false;
+}
+
+int s2_set_stream_from_stage1(harcgpu_ctx *c)
+{
+	free_stream(c);
+	cudaStream_t st = c->st;
+	const u32 m = c->n_matched;
+	c->m = m;
+	if (c->alloc(&c->sreads, (size_t)m * c->NW) || c->alloc(&c->s_order, m) || c->alloc(&c->s_rev, m) || c->alloc(&c->s_flag, m) ||
+	    c->alloc(&c->s_pos, m))
+		return -1;
+	if (m) {
+		DISPATCH_NW(c->NW, (gather_stream_kernel<NW><<<cdiv(m, 128), 128, 0, st>>>(c->reads, c->order, c->rev, m, c->L, c->sreads)));
+		CK(cudaGetLastError());
+		CK(cudaMemcpyAsync(c->s_order, c->order, 4 * (size_t)m, cudaMemcpyDeviceToDevice, st));
+		CK(cudaMemcpyAsync(c->s_rev, c->rev, m, cudaMemcpyDeviceToDevice, st));
+		CK(cudaMemcpyAsync(c->s_flag, c->flag, m, cudaMemcpyDeviceToDevice, st));
+		CK(cudaMemcpyAsync(c->s_pos, c->pos, m, cudaMemcpyDeviceToDevice, st));
+	}
+	c->stream_set = true;
+	return 0;
+}
+
+int s2_set_stream_host(harcgpu_ctx *c, const char *dna, const char *flag, const u8 *pos, const u32 *order, const char *rev, u32 m)
+{
+	free_stream(c);
+	cudaStream_t st = c->st;
+	c->m = m;
+	if (c->alloc(&c->sreads, (size_t)m * c->NW) || c->alloc(&c->s_order, m) || c->alloc(&c->s_rev, m) || c->alloc(&c->s_flag, m) ||
+	    c->alloc(&c->s_pos, m))
+		return -1;
+	if (m) {
+		char *d = nullptr;
+		size_t bytes = (size_t)m * (c->L + 1);
+		if (c->alloc(&d, bytes + 16)) return -1;
+		CK(cudaMemcpyAsync(d, dna, bytes, cudaMemcpyHostToDevice, st));
+		if (s1_packN(c, d, m, c->sreads, nullptr)) return -1;
+		CK(cudaMemcpyAsync(c->s_order, order, 4 * (size_t)m, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(c->s_rev, rev, m, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(c->s_flag, flag, m, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(c->s_pos, pos, m, cudaMemcpyHostToDevice, st));
+		CK(cudaStreamSynchronize(st));
+		c->release(d);
+	}
+	c->stream_set = true;
+	return 0;
+}
+
+// encoder.cpp:823-872 + 132-148
+int s2_load_pool(harcgpu_ctx *c, const char *s_ascii, const u32 *order_s, u32 n_s, const char *N_ascii, u32 n_N)
+{
+	free_pool(c);
+	cudaStream_t st = c->st;
+	const bool from_stage1 = (s_ascii == nullptr && order_s == nullptr && n_s == 0 && c->reordered);
+	if (from_stage1) n_s = c->n_single;
+	else if (n_s && (!s_ascii || !order_s)) { harcgpu_set_error("singleton reads and their order are both needed"); return -1; }
+	const u64 P64 = (u64)n_s + n_N;
+	if (P64 > 0xfffffff0ull) { harcgpu_set_error("pool too large"); return -1; }
+	const u32 P = (u32)P64;
+	c->n_s = n_s; c->n_N = n_N;
+	if (c->alloc(&c->pool, (size_t)P * c->NW) || c->alloc(&c->poolN, (size_t)P * c->NW) || c->alloc(&c->pool_order, P)) return -1;
+	if (P) CK(cudaMemsetAsync(c->poolN, 0, (size_t)P * c->NW * 8, st));
+	const size_t line = (size_t)c->L + 1;
+	if (n_s) {
+		if (from_stage1) {
+			DISPATCH_NW(c->NW, (gather_stream_kernel<NW><<<cdiv(n_s, 128), 128, 0, st>>>(c->reads, c->order_s, nullptr, n_s, c->L, c->pool)));
+			CK(cudaGetLastError());
+			CK(cudaMemcpyAsync(c->pool_order, c->order_s, 4 * (size_t)n_s, cudaMemcpyDeviceToDevice, st));
+		} else {
+			char *d = nullptr;
+			if (c->alloc(&d, n_s * line + 16)) return -1;
+			CK(cudaMemcpyAsync(d, s_ascii, n_s * line, cudaMemcpyHostToDevice, st));
+			if (s1_packN(c, d, n_s, c->pool, nullptr)) return -1;
+			CK(cudaMemcpyAsync(c->pool_order, order_s, 4 * (size_t)n_s, cudaMemcpyHostToDevice, st));
+			CK(cudaStreamSynchronize(st));
+			c->release(d);
+		}
+	}
+	if (n_N) {
+		char *d = nullptr;
+		if (c->alloc(&d, n_N * line + 16)) return -1;
+		CK(cudaMemcpyAsync(d, N_ascii, n_N * line, cudaMemcpyHostToDevice, st));
+		if (s1_packN(c, d, n_N, c->pool + (size_t)n_s * c->NW, c->poolN + (size_t)n_s * c->NW)) return -1;
+		iota_off_kernel<<<cdiv(n_N, 256), 256, 0, st>>>(c->pool_order + n_s, n_N); // order_s[i] = i - numreads_s (869-870)
+		CK(cudaGetLastError());
+		CK(cudaStreamSynchronize(st));
+		c->release(d);
+	}
+	// dictionary windows of encoder.cpp:132-145
+	int ds[2], de[2];
+	const int L = c->L;
+	if (L > 50) { ds[0] = 0; de[0] = 20; ds[1] = 21; de[1] = 41; }
+	else { ds[0] = 0; de[0] = 20 * L / 50; ds[1] = 20 * L / 50 + 1; de[1] = 41 * L / 50; }
+	for (int l = 0; l < 2; l++)
+		if (build_dict(c, c->d2[l], c->pool, c->poolN, P, c->NW, ds[l], de[l], 3)) return -1;
+	c->pool_set = true;
+	return 0;
+}
+
+int s2_encode(harcgpu_ctx *c)
+{
+	cudaStream_t st = c->st;
+	const u32 m = c->m, P = c->n_s + c->n_N, n_s = c->n_s;
+	const int L = c->L, NWv = c->NW, K = c->p.file_sets;
+	c->encoded = false;
+	// drop previous outputs
+	for (auto &s : c->sets) { c->release(s.seq); c->release(s.rev); }
+	c->sets.clear();
+	c->release(c->o_order); c->release(c->o_order_N); c->release(c->o_single); c->release(c->o_inputN);
+	c->o_order = c->o_order_N = nullptr; c->o_single = nullptr; c->o_inputN = nullptr;
+	for (void *q : c->s2_keep) c->release(q);
+	c->s2_keep.clear();
+	c->tic();
+
+	const u32 per = m ? 1 + (m - 1) / K : 1; // encoder.cpp:171
+	u32 *ns = nullptr, *ex = nullptr, *nat_idx = nullptr, *cs = nullptr, *cid = nullptr, *cstart = nullptr, *d_tot32 = nullptr;
+	u64 *inc = nullptr, *G = nullptr, *scan_tmp = nullptr, *d_tot64 = nullptr, *cons2 = nullptr;
+	u32 NC = 0;
+	u64 TOT = 0;
+	size_t scan_n = std::max<size_t>(std::max<size_t>(m, P), 1);
+	if (c->alloc(&d_tot32, 4) || c->alloc(&d_tot64, 2)) return -1;
+	if (m) {
+		if (c->alloc(&ns, m) || c->alloc(&ex, m) || c->alloc(&nat_idx, m) || c->alloc(&cs, m) || c->alloc(&cid, m) || c->alloc(&cstart, m) ||
+		    c->alloc(&inc, m) || c->alloc(&G, m))
+			return -1;
+	}
+	if (c->alloc(&scan_tmp, scan_tmp_elems(2 * scan_n + 64))) return -1;
+	if (m) {
+		natstart_kernel<<<cdiv(m, 256), 256, 0, st>>>(c->s_flag, m, per, ns);
+		if (exclusive_scan_u32(ns, ex, m, scan_tmp, nullptr, st)) return -1;
+		scatter_idx_kernel<<<cdiv(m, 256), 256, 0, st>>>(ns, ex, m, nat_idx);
+		cstart_kernel<<<cdiv(m, 256), 256, 0, st>>>(ns, ex, nat_idx, c->s_pos, m, L, cs, inc);
+		if (exclusive_scan_u32(cs, ex, m, scan_tmp, d_tot32, st)) return -1;
+		if (exclusive_scan_u64(inc, G, m, scan_tmp, d_tot64, st)) return -1;
+		finish_layout_kernel<<<cdiv(m, 256), 256, 0, st>>>(cs, ex, inc, G, m, cid, cstart);
+		CK(cudaGetLastError());
+		u64 tot = 0;
+		CK(cudaMemcpyAsync(&NC, d_tot32, 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(&tot, d_tot64, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		TOT = tot + L;
+	}
+	const size_t cwords = (size_t)((TOT + 31) / 32);
+	if (c->alloc(&cons2, cwords + 2)) return -1;
+	CK(cudaMemsetAsync(cons2 + cwords, 0, 16, st));
+	if (m) {
+		consensus_kernel<<<cdiv(cwords * 32, 256), 256, 0, st>>>(G, c->sreads, m, L, NWv, TOT, cons2);
+		CK(cudaGetLastError());
+	}
+
+	// ---- pool re-alignment
+	u64 *best = nullptr, *prio_u = nullptr, *iprio = nullptr;
+	u32 *af = nullptr, *exa = nullptr, *rid_u = nullptr, *irid = nullptr;
+	u32 M = 0;
+	if (c->alloc(&best, P)) return -1;
+	if (P) {
+		fill64_kernel<<<cdiv(P, 256), 256, 0, st>>>(best, P, NOBEST);
+		CK(cudaGetLastError());
+	}
+	if (P && m && TOT >= (u64)L) {
+		PoolArgs a;
+		a.G = G; a.cid = cid; a.cstart = cstart; a.m = m; a.NC = NC; a.per = per; a.TOT = TOT; a.cons2 = cons2;
+		a.pool = c->pool; a.poolN = c->poolN;
+		for (int l = 0; l < 2; l++) {
+			a.d[l].slots = c->d2[l].slots; a.d[l].ids = c->d2[l].ids; a.d[l].slot_mask = c->d2[l].slot_mask;
+			a.d[l].dstart = c->d2[l].bitpos / 3; a.d[l].dend = a.d[l].dstart + c->d2[l].nbits / 3 - 1;
+		}
+		a.L = L; a.thresh_s = c->p.thresh_s; a.maxsearch = c->p.maxsearch; a.best = best;
+		u64 nwin = TOT - L + 1;
+		DISPATCH_NW(NWv, (pool_probe_kernel<NW><<<cdiv(nwin, 128), 128, 0, st>>>(a)));
+		CK(cudaGetLastError());
+		if (c->alloc(&af, P) || c->alloc(&exa, P) || c->alloc(&prio_u, P) || c->alloc(&rid_u, P)) return -1;
+		aligned_flag_kernel<<<cdiv(P, 256), 256, 0, st>>>(best, P, af);
+		if (exclusive_scan_u32(af, exa, P, scan_tmp, d_tot32, st)) return -1;
+		aligned_compact_kernel<<<cdiv(P, 256), 256, 0, st>>>(best, af, exa, P, prio_u, rid_u);
+		CK(cudaGetLastError());
+		CK(cudaMemcpyAsync(&M, d_tot32, 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+	}
+	if (c->alloc(&iprio, M) || c->alloc(&irid, M)) return -1;
+	if (M) {
+		int end_bit = 3;
+		while (end_bit < 64 && (TOT >> (end_bit - 2)) != 0) end_bit++;
+		size_t tb = 0;
+		void *cub_tmp = nullptr;
+		CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, prio_u, iprio, rid_u, irid, (int64_t)M, 0, end_bit, st));
+		if (c->alloc((char **)&cub_tmp, tb)) return -1;
+		CK(cub::DeviceRadixSort::SortPairs(cub_tmp, tb, prio_u, iprio, rid_u, irid, (int64_t)M, 0, end_bit, st));
+		CK(cudaStreamSynchronize(st));
+		c->release(cub_tmp);
+	}
+
+	// ---- merged list
+	const u64 F = (u64)m + M;
+	u32 *f_src = nullptr, *isN = nullptr, *exN = nullptr, *ordv = nullptr;
+	u8 *f_kind = nullptr, *posb = nullptr, *revc = nullptr, *noisepos = nullptr;
+	u64 *f_col = nullptr, *nm1 = nullptr, *noff = nullptr;
+	char *noise = nullptr;
+	if (c->alloc(&f_src, F) || c->alloc(&f_kind, F) || c->alloc(&f_col, F) || c->alloc(&nm1, F) || c->alloc(&noff, F + 1) ||
+	    c->alloc(&posb, F) || c->alloc(&revc, F + 8) || c->alloc(&isN, F) || c->alloc(&exN, F) || c->alloc(&ordv, F))
+		return -1;
+	c->release(scan_tmp);
+	if (c->alloc(&scan_tmp, scan_tmp_elems(2 * std::max<u64>(std::max<u64>(F, P), 1) + 64))) return -1;
+	u64 NB = 0;
+	u32 FN = 0;
+	if (m) {
+		place_orig_kernel<<<cdiv(m, 256), 256, 0, st>>>(G, m, iprio, M, f_src, f_kind, f_col);
+		CK(cudaGetLastError());
+	}
+	if (M) {
+		place_ins_kernel<<<cdiv(M, 256), 256, 0, st>>>(G, m, iprio, irid, M, f_src, f_kind, f_col);
+		CK(cudaGetLastError());
+	}
+	EmitArgs ea;
+	ea.f_src = f_src; ea.f_kind = f_kind; ea.f_col = f_col; ea.F = F; ea.sreads = c->sreads; ea.cs = cs; ea.s_order = c->s_order;
+	ea.s_rev = c->s_rev; ea.pool = c->pool; ea.poolN = c->poolN; ea.pool_order = c->pool_order; ea.n_s = n_s; ea.cons2 = cons2; ea.L = L;
+	ea.nm1 = nm1; ea.posb = posb; ea.revc = revc; ea.isN = isN; ea.ordv = ordv; ea.noff = noff; ea.exN = exN;
+	ea.noise = nullptr; ea.noisepos = nullptr; ea.o_order = nullptr; ea.o_order_N = nullptr;
+	if (F) {
+		DISPATCH_NW(NWv, (emit_count_kernel<NW><<<cdiv(F, 128), 128, 0, st>>>(ea)));
+		CK(cudaGetLastError());
+		if (exclusive_scan_u64(nm1, noff, F, scan_tmp, d_tot64, st)) return -1;
+		if (exclusive_scan_u32(isN, exN, F, scan_tmp, d_tot32, st)) return -1;
+		CK(cudaMemcpyAsync(&NB, d_tot64, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(&FN, d_tot32, 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		CK(cudaMemcpyAsync(noff + F, d_tot64, 8, cudaMemcpyDeviceToDevice, st));
+	} else {
+		CK(cudaMemsetAsync(noff, 0, 8, st));
+	}
+	// ---- unaligned pool reads
+	u32 *uf = nullptr, *exU = nullptr, *ulist = nullptr;
+	u32 U = 0, U_s = 0;
+	if (c->alloc(&uf, P) || c->alloc(&exU, (size_t)P + 1) || c->alloc(&ulist, P)) return -1;
+	if (P) {
+		unaligned_flag_kernel<<<cdiv(P, 256), 256, 0, st>>>(best, P, uf);
+		if (exclusive_scan_u32(uf, exU, P, scan_tmp, d_tot32, st)) return -1;
+		CK(cudaMemcpyAsync(exU + P, d_tot32, 4, cudaMemcpyDeviceToDevice, st));
+		CK(cudaMemcpyAsync(&U, d_tot32, 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(&U_s, exU + n_s, 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+	}
+	const u32 U_N = U - U_s;
+	const u64 Fc = F - FN;
+	const u64 n_order = Fc + U_s, n_order_N = (u64)FN + U_N;
+	if (c->alloc(&c->o_order, n_order) || c->alloc(&c->o_order_N, n_order_N) || c->alloc(&noise, NB) || c->alloc(&noisepos, NB - F + 1))
+		return -1;
+	if (F) {
+		ea.noise = noise; ea.noisepos = noisepos; ea.o_order = c->o_order; ea.o_order_N = c->o_order_N;
+		DISPATCH_NW(NWv, (emit_write_kernel<NW><<<cdiv(F, 128), 128, 0, st>>>(ea)));
+		CK(cudaGetLastError());
+	}
+	const u64 sbases = (u64)U_s * L, sbytes = sbases / 4, stail = sbases % 4;
+	const u64 nbytesN = (u64)U_N * (L + 1);
+	char *d_tail = nullptr;
+	if (c->alloc(&c->o_single, sbytes) || c->alloc(&c->o_inputN, nbytesN) || c->alloc(&d_tail, 16 * (size_t)(K + 1))) return -1;
+	CK(cudaMemsetAsync(d_tail, 0, 16 * (size_t)(K + 1), st));
+	if (P) {
+		unaligned_kernel<<<cdiv(P, 256), 256, 0, st>>>(uf, exU, P, n_s, U_s, c->pool_order, ulist, c->o_order + Fc, c->o_order_N + FN);
+		CK(cudaGetLastError());
+		if (sbases) {
+			pack_singleton_kernel<<<cdiv(sbytes + 1, 256), 256, 0, st>>>(c->pool, ulist, L, NWv, sbases, sbytes, c->o_single, d_tail + 16 * (size_t)K);
+			CK(cudaGetLastError());
+		}
+		if (nbytesN) {
+			unaligned_N_kernel<<<cdiv(nbytesN, 256), 256, 0, st>>>(c->pool, c->poolN, ulist + U_s, L, NWv, nbytesN, c->o_inputN);
+			CK(cudaGetLastError());
+		}
+	}
+
+	// ---- per file set views (encoder.cpp:169-196, 512-581)
+	c->sets.resize(K);
+	std::vector<u64> h_fs(K + 1), h_col(K + 1), h_no(K + 1);
+	for (int k = 0; k <= K; k++) {
+		u64 a = std::min<u64>((u64)k * per, m);
+		if (k == K || a >= m) { h_fs[k] = F; h_col[k] = TOT; h_no[k] = NB; continue; }
+		u64 g = 0;
+		CK(cudaMemcpyAsync(&g, G + a, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		h_col[k] = g;
+		// inserted reads with column < g precede original a; none can sit at column >= g of an earlier contig
+		u64 lo = 0;
+		if (M) {
+			// binary search on the device array through small copies
+			u64 l0 = 0, hi = M;
+			while (l0 < hi) {
+				u64 mid = (l0 + hi) >> 1, pv = 0;
+				CK(cudaMemcpyAsync(&pv, iprio + mid, 8, cudaMemcpyDeviceToHost, st));
+				CK(cudaStreamSynchronize(st));
+				if ((pv >> 2) < g) l0 = mid + 1; else hi = mid;
+			}
+			lo = l0;
+		}
+		h_fs[k] = a + lo;
+		CK(cudaMemcpyAsync(&h_no[k], noff + h_fs[k], 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+	}
+	for (int k = 0; k < K; k++) {
+		SetOut &s = c->sets[k];
+		const u64 e0 = h_fs[k], e1 = h_fs[k + 1], cnt = e1 - e0;
+		const u64 col0 = h_col[k], col1 = h_col[k + 1], ncol = col1 - col0;
+		s.pos = posb + e0; s.pos_bytes = cnt;
+		s.noise = noise + h_no[k]; s.noise_bytes = h_no[k + 1] - h_no[k];
+		s.noisepos = noisepos + (h_no[k] - e0); s.noisepos_bytes = s.noise_bytes - cnt;
+		s.seq_bytes = ncol / 4; s.seq_ntail = (u32)(ncol % 4);
+		s.rev_bytes = cnt / 8; s.rev_ntail = (u32)(cnt % 8);
+		if (c->alloc(&s.seq, s.seq_bytes) || c->alloc(&s.rev, s.rev_bytes)) return -1;
+		if (s.seq_bytes) pack_seq_kernel<<<cdiv(s.seq_bytes, 256), 256, 0, st>>>(cons2, col0, s.seq_bytes, s.seq);
+		if (s.rev_bytes) pack_rev_kernel<<<cdiv(s.rev_bytes, 256), 256, 0, st>>>(revc, e0, s.rev_bytes, s.rev);
+		if (s.seq_ntail || s.rev_ntail) tails_kernel<<<1, 32, 0, st>>>(cons2, col1, s.seq_ntail, revc, e1, s.rev_ntail, d_tail + 16 * (size_t)k);
+		CK(cudaGetLastError());
+	}
+	std::vector<char> h_tail(16 * (size_t)(K + 1));
+	CK(cudaMemcpyAsync(h_tail.data(), d_tail, h_tail.size(), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	for (int k = 0; k < K; k++) {
+		memcpy(c->sets[k].seq_tail, &h_tail[16 * (size_t)k], 4);
+		memcpy(c->sets[k].rev_tail, &h_tail[16 * (size_t)k + 4], 8);
+	}
+	memcpy(c->single_tail, &h_tail[16 * (size_t)K], 4);
+	c->toc("encode");
+
+	c->esz.n_order = (u32)n_order; c->esz.n_order_N = (u32)n_order_N;
+	c->esz.singleton_bytes = sbytes; c->esz.singleton_tail = stail; c->esz.input_N_bytes = nbytesN;
+	c->esz.aligned_singletons = n_s - U_s; c->esz.aligned_N = c->n_N - U_N;
+	c->s2_keep.push_back(posb); c->s2_keep.push_back(noise); c->s2_keep.push_back(noisepos);
+	void *tmp[] = { ns, ex, nat_idx, cs, cid, cstart, inc, G, scan_tmp, d_tot32, d_tot64, cons2, best, prio_u, iprio, af, exa, rid_u, irid,
+	                f_src, f_kind, f_col, nm1, noff, revc, isN, exN, ordv, uf, exU, ulist, d_tail };
+	for (void *q : tmp) c->release(q);
+	c->encoded = true;
+	return 0;
+}
