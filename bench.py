@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- Mreads/s of HARC's reorder+encode hot path (stage I + stage II) on B200.
+
+A "step" is one full pass of the hot path over one synthetic FASTQ's worth of reads: 2-bit pack -> dictionary build
+-> chain walk -> finalize -> stage II (pool dictionaries, consensus, re-alignment, emission, packbits).
+Workload at N=1: BASELINE.json configs[1] -- 35 M x 100 bp reads, 1 % substitutions incl. N (gen_fastq_noRC -e read
+model), from a synthetic 50 Mbp genome.  At N>1 every rank owns an independent read set of that size (weak scaling,
+no data-path collective); `value` = reads of all ranks / max-over-ranks time.
+
+  value : device-timed, inputs (ASCII reads) already resident in HBM.
+  e2e   : the same pass through the C ABI with HOST buffers: H2D of the reads and D2H of every stage II stream
+          are inside the timed region.
+  --impl reference : the reference's own reorder.out + encoder.out (oracle/_ref, built unmodified from the
+          reference sources) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+import numpy as np
+
+METRIC = "Mreads/s reorder+encode (100bp)"
+L = 100
+
+
+def algorithmic_bytes_per_clean_read(genome, n_clean):
+    """walk-kernel share of B_alg = 32 B per dictionary probe x P + candidate fetch R + claim RMW 4 B +
+    8 B record, with P = 2*numdict*(g+1) + numdict, g = min(maxmatch, genome/N_clean)."""
+    g = min(L // 2, genome / max(1, n_clean))
+    P = 2 * 2 * (g + 1) + 2
+    return 32.0 * P + 32 + 4 + 8, P
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop = threading.Event()
+        self.sm = []
+        self.smmax = 0
+        self.reasons = set()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=5).stdout.decode().strip()
+                f = [x.strip() for x in o.split(",")]
+                self.sm.append(float(f[0]))
+                self.smmax = float(f[1])
+                for nme, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nme)
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smmax or None,
+                "reasons": sorted(self.reasons)}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path, all host threads it can use, bounded sample."""
+    import refrun as R
+    import workload as W
+    avail = R.ref_threads_available(L)
+    if not avail:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+        return
+    ncpu = os.cpu_count() or 1
+    T = max([t for t in avail if t <= ncpu] or [min(avail)])
+    n = int(args.ref_reads)
+    genome = int(args.genome * (n / args.reads))
+    w = W.make(n, L, genome, rc=False, errors=True, seed=args.seed)
+    times = []
+    for it in range(args.warmup + args.steps):
+        tmp = tempfile.mkdtemp(prefix="harcref")
+        try:
+            W.write_dir(w, tmp)
+            t1, _ = R.reorder(tmp, L, T)
+            t2, _ = R.encoder(tmp, L, T)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        if it >= args.warmup:
+            times.append(t1 + t2)
+    ms = 1000.0 * sum(times) / len(times)
+    val = n / (ms / 1000.0) / 1e6
+    sample = "%d reads x %d bp, %d bp genome (same coverage and error model as the workload), reorder.out + encoder.out wall time incl. their file I/O" % (n, L, genome)
+    print(json.dumps({
+        "metric": METRIC, "value": val, "unit": "Mreads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "impl": "reference",
+        "config": {"workload": "configs[1]: 35M x 100bp, 1% substitutions incl. N (gen_fastq_noRC -e model), 50 Mbp genome; timed on a bounded sample", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Mreads/s", "cores": T, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": "Mreads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline(args):
+    import refrun as R
+    import workload as W
+    avail = R.ref_threads_available(L)
+    if not avail:
+        return None
+    ncpu = os.cpu_count() or 1
+    T = max([t for t in avail if t <= ncpu] or [min(avail)])
+    n = int(args.ref_reads)
+    genome = int(args.genome * (n / args.reads))
+    w = W.make(n, L, genome, rc=False, errors=True, seed=args.seed)
+    tmp = tempfile.mkdtemp(prefix="harcref")
+    try:
+        W.write_dir(w, tmp)
+        t1, _ = R.reorder(tmp, L, T)
+        t2, _ = R.encoder(tmp, L, T)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return {"value": n / (t1 + t2) / 1e6, "unit": "Mreads/s", "cores": T, "kind": "reference",
+            "sample": "%d reads x %d bp, %d bp genome (same coverage/error model), reorder.out %.1fs + encoder.out %.1fs incl. file I/O"
+                      % (n, L, genome, t1, t2)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=float, default=35e6)
+    ap.add_argument("--genome", type=float, default=50e6)
+    ap.add_argument("--ref-reads", type=float, default=3.5e6)
+    ap.add_argument("--walkers", type=int, default=0)
+    ap.add_argument("--file-sets", type=int, default=1)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer pass")
+    args = ap.parse_args()
+    args.reads = int(args.reads)
+    args.genome = int(args.genome)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args)
+        return
+
+    import torch
+    import harc_b200
+    import workload as W
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- workload: every rank owns an independent read set (seed differs per rank)
+    w = W.make(args.reads, L, args.genome, rc=False, errors=True, seed=args.seed + 7919 * rank)
+    n_clean, n_N = w["n_clean"], w["n_N"]
+    h_clean = torch.from_numpy(w["clean"]).pin_memory()
+    h_N = torch.from_numpy(w["withN"]).pin_memory()
+    d_clean = torch.empty(h_clean.numel() + 16, dtype=torch.uint8, device="cuda")
+    d_N = torch.empty(h_N.numel() + 16, dtype=torch.uint8, device="cuda")
+    d_clean[: h_clean.numel()].copy_(h_clean)
+    d_N[: h_N.numel()].copy_(h_N)
+    torch.cuda.synchronize()
+    del w["all"]
+
+    ctx = harc_b200.HarcGpu(L, device=local, walkers=args.walkers, file_sets=args.file_sets)
+    stream = torch.cuda.ExternalStream(ctx.stream())
+    phases = ["pack", "dict", "walk", "finalize", "pooldict", "encode"]
+
+    def step_device():
+        ctx.load_reads_device(d_clean.data_ptr(), n_clean)
+        ctx.build_dicts()
+        ctx.reorder()
+        ctx.load_pool_device(d_N.data_ptr(), n_N)
+        return ctx.encode()
+
+    d2h = [0]
+
+    host_ms = {}
+
+    def step_host():
+        t = [time.perf_counter()]
+
+        def lap(name):
+            t.append(time.perf_counter())
+            host_ms[name] = host_ms.get(name, 0.0) + 1000.0 * (t[-1] - t[-2])
+        ctx.load_reads(h_clean.numpy(), n_clean)
+        lap("load_reads(H2D+pack)")
+        ctx.reorder()
+        lap("reorder")
+        ctx.load_pool(None, None, h_N.numpy())
+        lap("load_pool(H2D+dict)")
+        ctx.encode()
+        lap("encode")
+        nbytes = 0
+        for k in range(args.file_sets):
+            s = ctx.get_set(k)
+            nbytes += sum(v.nbytes for v in s.values())
+        g = ctx.get_globals()
+        nbytes += sum(v.nbytes for v in g.values())
+        lap("get outputs(D2H)")
+        d2h[0] = nbytes
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, sampler=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ph = {p: 0.0 for p in phases}
+        if sampler:
+            sampler.start()
+        l0 = harc_b200.launch_count()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+            for p in phases:
+                ph[p] += max(0.0, ctx.last_ms(p))
+        e1.record(stream)
+        barrier()
+        if sampler:
+            sampler.stop.set()
+        ms = e0.elapsed_time(e1) / steps
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, {p: ph[p] / steps for p in phases}, (harc_b200.launch_count() - l0) // steps
+
+    for _ in range(args.warmup):
+        es = step_device()
+    sampler = ClockSampler(local)
+    ms_dev, ph, launches = timed(step_device, args.steps, sampler)
+    cnt = ctx.counters()
+    m, s, u = ctx.reorder_counts()
+    if args.no_e2e:
+        ms_e2e = float("nan")
+    else:
+        step_host()  # warm the host path
+        step_host()
+        host_ms.clear()
+        ms_e2e, _, _ = timed(step_host, args.steps)
+
+    total_reads = (n_clean + n_N) * world
+    value = total_reads / (ms_dev / 1000.0) / 1e6
+    e2e = total_reads / (ms_e2e / 1000.0) / 1e6
+    if rank != 0:
+        ctx.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    balg, P = algorithmic_bytes_per_clean_read(args.genome, n_clean)
+    walk_ms = ph["walk"]
+    achieved = n_clean * balg / (walk_ms / 1000.0) / 1e9 if walk_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "walk_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    out = {
+        "metric": METRIC, "value": value, "unit": "Mreads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "configs[1]: %d x %dbp reads, 1%% substitutions incl. N (gen_fastq_noRC -e model), %d bp synthetic genome, per GPU"
+                               % (args.reads, L, args.genome),
+                   "reads_per_gpu": args.reads, "clean_reads": n_clean, "reads_with_N": n_N, "walkers": ctx.p.walkers or "auto",
+                   "file_sets": args.file_sets, "parallelism": "1 independent read set per GPU" if world > 1 else "single GPU",
+                   "l2": "inputs (%.1f GB ASCII, %.1f GB packed) exceed the 126 MB L2; no explicit flush" % ((n_clean + n_N) * 101 / 1e9, n_clean * 32 / 1e9)},
+        "phases_ms": ph,
+        "stage1": {"matched": m, "singletons": s, "chain_heads": u, "probes_per_read": cnt["probes"] / max(1, cnt["steps"]),
+                   "compares_per_read": cnt["compares"] / max(1, cnt["steps"]), "claim_fails": cnt["claim_fails"]},
+        "stage2": {"aligned_singletons": es.aligned_singletons, "aligned_N": es.aligned_N},
+        "roofline": {"bound": "hbm", "kernel": "walk_kernel<4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "algorithmic_bytes_per_clean_read": balg, "model_probes_per_read": P,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+        "e2e": {"value": e2e, "unit": "Mreads/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h_clean.numel() + h_N.numel()),
+                "d2h_bytes_per_step": int(d2h[0]),
+                "host_wall_ms": {k: v / args.steps for k, v in host_ms.items()}},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            out["cpu_baseline"] = cpu_baseline(args)
+        except Exception as ex:  # the reference binaries are a reported baseline, never a dependency of the GPU number
+            out["cpu_baseline"] = {"error": str(ex)[:200]}
+    print(json.dumps(out))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -18,6 +18,7 @@ EXPORTS = [
     "harcgpu_reorder_counts", "harcgpu_get_reorder", "harcgpu_get_reordered_reads", "harcgpu_get_counters",
     "harcgpu_set_stream", "harcgpu_load_pool", "harcgpu_encode", "harcgpu_get_encode_sizes", "harcgpu_get_set_sizes",
     "harcgpu_get_set", "harcgpu_get_globals", "harcgpu_reorder_dir", "harcgpu_encode_dir", "harcgpu_last_ms", "harcgpu_stream",
+    "harcgpu_load_pool_device", "harcgpu_launch_count",
 ]
 
 
@@ -77,6 +78,8 @@ def load_library():
     lib.harcgpu_set_stream.argtypes = [vp, vp, vp, vp, vp, vp, u32]
     lib.harcgpu_load_pool.argtypes = [vp, vp, vp, u32, vp, u32]
     lib.harcgpu_encode.argtypes = [vp]
+    lib.harcgpu_load_pool_device.argtypes = [vp, vp, u32]
+    lib.harcgpu_launch_count.restype = ctypes.c_uint64
     lib.harcgpu_get_encode_sizes.argtypes = [vp, ctypes.POINTER(EncodeSizes)]
     lib.harcgpu_get_set_sizes.argtypes = [vp, ctypes.c_int, ctypes.POINTER(SetSizes)]
     lib.harcgpu_get_set.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
@@ -85,6 +88,10 @@ def load_library():
     lib.harcgpu_encode_dir.argtypes = [vp, cp]
     _lib = lib
     return lib
+
+
+def launch_count():
+    return int(load_library().harcgpu_launch_count())
 
 
 class HarcError(RuntimeError):
@@ -205,6 +212,12 @@ class HarcGpu:
         nN = 0 if N_ascii is None else len(N_ascii) // (self.L + 1)
         self._keep3 = (singleton_ascii, order_s, N_ascii)
         self._ck(self.lib.harcgpu_load_pool(self.h, _ptr(singleton_ascii), _ptr(order_s), ns, _ptr(N_ascii), nN))
+
+    def load_pool_device(self, dptr, n_N):
+        self._ck(self.lib.harcgpu_load_pool_device(self.h, ctypes.c_void_p(dptr), n_N))
+
+    def stream(self):
+        return self.lib.harcgpu_stream(self.h)
 
     def encode(self):
         self._ck(self.lib.harcgpu_encode(self.h))

@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 
+unsigned long long g_harcgpu_launches = 0;
 static thread_local char g_err[1024] = "";
 void harcgpu_set_error(const char *fmt, ...)
 {
@@ -18,6 +19,7 @@ void harcgpu_set_error(const char *fmt, ...)
 extern "C" {
 
 const char *harcgpu_last_error(void) { return g_err; }
+uint64_t harcgpu_launch_count(void) { return g_harcgpu_launches; }
 
 int harcgpu_device_count(void)
 {
@@ -72,6 +74,12 @@ int harcgpu_create(int device, const harcgpu_params *p, harcgpu_ctx **out)
 	c->NW3 = (3 * c->L + 63) / 64;
 	memset(&c->esz, 0, sizeof c->esz);
 	CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+	{
+		cudaMemPool_t pool;
+		CK(cudaDeviceGetDefaultMemPool(&pool, device));
+		unsigned long long keep = ~0ull; // keep freed blocks cached in the pool between passes
+		CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+	}
 	CK(cudaEventCreate(&c->ev0));
 	CK(cudaEventCreate(&c->ev1));
 	if (c->alloc(&c->counters, 8) || c->alloc(&c->gpos, 1)) return -1;
@@ -85,7 +93,8 @@ void harcgpu_destroy(harcgpu_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->st);
-	for (void *q : c->allocs) cudaFree(q);
+	for (void *q : c->allocs) cudaFreeAsync(q, c->st);
+	cudaStreamSynchronize(c->st);
 	cudaEventDestroy(c->ev0);
 	cudaEventDestroy(c->ev1);
 	cudaStreamDestroy(c->st);
@@ -247,6 +256,14 @@ int harcgpu_load_pool(harcgpu_ctx *c, const char *s_ascii, const uint32_t *order
 	if (!c || (n_N && !N_ascii)) { harcgpu_set_error("null argument"); return -1; }
 	CK(cudaSetDevice(c->device));
 	return s2_load_pool(c, s_ascii, order_s, n_s, N_ascii, n_N);
+}
+
+int harcgpu_load_pool_device(harcgpu_ctx *c, const void *d_N_ascii, uint32_t n_N)
+{
+	if (!c || (n_N && !d_N_ascii)) { harcgpu_set_error("null argument"); return -1; }
+	if (!c->reordered) { harcgpu_set_error("harcgpu_load_pool_device needs the singletons of harcgpu_reorder on this context"); return -1; }
+	CK(cudaSetDevice(c->device));
+	return s2_load_pool_dev(c, d_N_ascii, n_N);
 }
 
 int harcgpu_encode(harcgpu_ctx *c)

@@ -21,6 +21,10 @@ void harcgpu_set_error(const char *fmt, ...);
 		}                                                                                          \
 	} while (0)
 
+// every kernel launch of this library bumps the counter (bench.py reports it as gpu_launches)
+extern unsigned long long g_harcgpu_launches;
+#define KL (g_harcgpu_launches++, 0u)
+
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 // ---- bit helpers shared by the kernels -------------------------------------------------------------------

@@ -62,13 +62,15 @@ struct harcgpu_ctx {
 	u8 *o_single = nullptr; char single_tail[4];
 	char *o_inputN = nullptr;
 
+	// Stream-ordered allocations from the device's default pool (release threshold raised in harcgpu_create), so the
+	// many short-lived work buffers of a pass cost no cudaMalloc/cudaFree round trips after the first pass.
 	template <typename T> int alloc(T **out, size_t count)
 	{
 		void *q = nullptr;
 		size_t bytes = (count ? count : 1) * sizeof(T);
-		cudaError_t e = cudaMalloc(&q, bytes);
+		cudaError_t e = cudaMallocAsync(&q, bytes, st);
 		if (e != cudaSuccess) {
-			harcgpu_set_error("cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+			harcgpu_set_error("cudaMallocAsync(%zu bytes): %s", bytes, cudaGetErrorString(e));
 			*out = nullptr;
 			return -1;
 		}
@@ -81,7 +83,7 @@ struct harcgpu_ctx {
 		if (!q) return;
 		for (size_t i = 0; i < allocs.size(); i++)
 			if (allocs[i] == q) { allocs[i] = allocs.back(); allocs.pop_back(); break; }
-		cudaFree(q);
+		cudaFreeAsync(q, st);
 	}
 	void tic() { cudaEventRecord(ev0, st); }
 	void toc(const char *phase)
@@ -105,4 +107,5 @@ int s1_unpack_reads(harcgpu_ctx *c, const u64 *reads, const u32 *order, const u8
 int s2_set_stream_from_stage1(harcgpu_ctx *c);
 int s2_set_stream_host(harcgpu_ctx *c, const char *dna, const char *flag, const u8 *pos, const u32 *order, const char *rev, u32 n);
 int s2_load_pool(harcgpu_ctx *c, const char *s_ascii, const u32 *order_s, u32 n_s, const char *N_ascii, u32 n_N);
+int s2_load_pool_dev(harcgpu_ctx *c, const void *d_N_ascii, u32 n_N);
 int s2_encode(harcgpu_ctx *c);

@@ -76,15 +76,15 @@ int scan_rec(const T *in, T *out, size_t n, T *tmp, T *total, cudaStream_t st)
 	}
 	size_t nt = (n + TILE - 1) / TILE;
 	if (nt == 1) {
-		tile_scan<T><<<1, TPB, 0, st>>>(in, out, nullptr, n, total);
+		tile_scan<T><<<KL + 1, TPB, 0, st>>>(in, out, nullptr, n, total);
 		CK(cudaGetLastError());
 		return 0;
 	}
 	T *sums = tmp, *rest = tmp + nt;
-	tile_sums<T><<<(unsigned)nt, TPB, 0, st>>>(in, sums, n);
+	tile_sums<T><<<KL + (unsigned)nt, TPB, 0, st>>>(in, sums, n);
 	CK(cudaGetLastError());
 	if (scan_rec<T>(sums, sums, nt, rest, nullptr, st)) return -1;
-	tile_scan<T><<<(unsigned)nt, TPB, 0, st>>>(in, out, sums, n, total);
+	tile_scan<T><<<KL + (unsigned)nt, TPB, 0, st>>>(in, out, sums, n, total);
 	CK(cudaGetLastError());
 	return 0;
 }

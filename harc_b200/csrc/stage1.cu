@@ -154,7 +154,7 @@ int s1_pack_reads(harcgpu_ctx *c, const void *d_ascii, u32 n)
 	if (n == 0) return 0;
 	size_t smem = (size_t)PACK_RPB * (c->L + 1);
 	smem = (smem + 15) / 16 * 16;
-	pack_kernel<false><<<cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, c->reads, nullptr);
+	pack_kernel<false><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, c->reads, nullptr);
 	CK(cudaGetLastError());
 	return 0;
 }
@@ -164,15 +164,15 @@ int s1_packN(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *out2, u64 *outN)
 	if (n == 0) return 0;
 	size_t smem = (size_t)PACK_RPB * (c->L + 1);
 	smem = (smem + 15) / 16 * 16;
-	if (outN) pack_kernel<true><<<cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, out2, outN);
-	else pack_kernel<false><<<cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, out2, nullptr);
+	if (outN) pack_kernel<true><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, out2, outN);
+	else pack_kernel<false><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, out2, nullptr);
 	CK(cudaGetLastError());
 	return 0;
 }
 int s1_unpack_reads(harcgpu_ctx *c, const u64 *reads, const u32 *order, const u8 *rev, u32 cnt, char *d_out)
 {
 	if (cnt == 0) return 0;
-	unpack_kernel<<<cdiv(cnt, PACK_RPB), 256, 0, c->st>>>(reads, order, rev, cnt, c->L, c->NW, d_out);
+	unpack_kernel<<<KL + cdiv(cnt, PACK_RPB), 256, 0, c->st>>>(reads, order, rev, cnt, c->L, c->NW, d_out);
 	CK(cudaGetLastError());
 	return 0;
 }
@@ -206,15 +206,15 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 	if (c->alloc(&k_in, n) || c->alloc(&k_out, n) || c->alloc(&id_in, n) || c->alloc(&head, n) || c->alloc(&binidx, n) ||
 	    c->alloc(&scan_tmp, scan_tmp_elems(n)) || c->alloc(&d_total, 1))
 		return -1;
-	if (bits == 2) keys_kernel<<<cdiv(n, 256), 256, 0, st>>>(reads, n, words, bitpos, nbits, k_in, id_in);
-	else keys3_kernel<<<cdiv(n, 256), 256, 0, st>>>(reads, readsN, n, words, ds, de, k_in, id_in);
+	if (bits == 2) keys_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(reads, n, words, bitpos, nbits, k_in, id_in);
+	else keys3_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(reads, readsN, n, words, ds, de, k_in, id_in);
 	CK(cudaGetLastError());
 	size_t tb = 0;
 	CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, id_in, d.ids, (int64_t)n, 0, nbits, st));
 	if (c->alloc((char **)&cub_tmp, tb)) return -1;
 	// LSD radix sort is stable and ids start ascending, so ids stay ascending inside a bin (reorder.cpp:371-384)
 	CK(cub::DeviceRadixSort::SortPairs(cub_tmp, tb, k_in, k_out, id_in, d.ids, (int64_t)n, 0, nbits, st));
-	heads_kernel<<<cdiv(n, 256), 256, 0, st>>>(k_out, n, head);
+	heads_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(k_out, n, head);
 	CK(cudaGetLastError());
 	if (exclusive_scan_u32(head, binidx, n, scan_tmp, d_total, st)) return -1;
 	u32 nk = 0;
@@ -222,14 +222,14 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 	CK(cudaStreamSynchronize(st));
 	d.numkeys = nk;
 	if (c->alloc(&d.keys, nk) || c->alloc(&d.start, (size_t)nk + 1)) return -1;
-	bins_kernel<<<cdiv(n, 256), 256, 0, st>>>(k_out, head, binidx, n, nk, d.keys, d.start);
+	bins_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(k_out, head, binidx, n, nk, d.keys, d.start);
 	CK(cudaGetLastError());
 	u64 cap = 16;
 	while (cap < 2ull * nk) cap <<= 1;
 	d.slot_mask = (u32)(cap - 1);
 	if (c->alloc(&d.slots, cap)) return -1;
 	CK(cudaMemsetAsync(d.slots, 0, cap * sizeof(ulonglong2), st));
-	insert_kernel<<<cdiv(nk, 256), 256, 0, st>>>(d.keys, d.start, nk, d.slots, d.slot_mask);
+	insert_kernel<<<KL + cdiv(nk, 256), 256, 0, st>>>(d.keys, d.start, nk, d.slots, d.slot_mask);
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(st));
 	c->release(k_in); c->release(k_out); c->release(id_in); c->release(head); c->release(binidx);
@@ -255,7 +255,7 @@ struct WalkArgs {
 	DictView d[2];
 	int kbits[2];
 	u32 *claim;
-	long long *gpos;
+	u32 *stripe_done;
 	u32 walkers;
 	// record log
 	u64 *recs;
@@ -266,23 +266,11 @@ struct WalkArgs {
 	u64 *counters;
 };
 
-// spread the 32 bits of x to the even bit positions of a 64-bit word
-__device__ __forceinline__ u64 spread32(u32 x)
-{
-	u64 v = x;
-	v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
-	v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
-	v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
-	v = (v | (v << 2)) & 0x3333333333333333ull;
-	v = (v | (v << 1)) & 0x5555555555555555ull;
-	return v;
-}
-
 template <int NW>
-struct WalkSmem {
+struct alignas(16) WalkSmem {
 	u64 ref[NW];   // consensus of the current window, 2 bits/base (reorder.cpp:466)
 	u64 rref[NW];  // its reverse complement
-	u64 cur[NW];   // the read just appended
+	u64 cur[NW + (NW & 1)]; // the read just appended (padded so the vote counts that follow stay 16-byte aligned)
 };
 
 template <int NW>
@@ -299,49 +287,54 @@ __device__ __forceinline__ void load_read(const u64 *__restrict__ reads, u32 rid
 	}
 }
 
-// updaterefcount (reorder.cpp:863-915): vote counts live in a circular buffer (origin `head`) instead of being
-// shifted; lane handles bases lane, lane+32, ...; ref/rref words are rebuilt with ballots.
+__device__ __forceinline__ u64 revpairs64_w(u64 x) // reverse the order of the 32 base pairs of a word
+{
+	u64 y = __brevll(x);
+	return ((y & 0x5555555555555555ull) << 1) | ((y >> 1) & 0x5555555555555555ull);
+}
+
+// updaterefcount (reorder.cpp:863-915).  Vote counts live in a circular buffer (origin `head`) of uint4 {A,C,G,T} per
+// position instead of being shifted; lane handles bases lane, lane+32, ...; the consensus word t is assembled with
+// two warp OR-reductions (lanes 0-15 -> low half, 16-31 -> high half); the reverse complement is derived from the
+// finished words by lanes 0..NW-1 (pair reversal + shift + complement).
 template <int NW>
-__device__ __forceinline__ void update_ref(WalkSmem<NW> &s, u32 *cnt, u8 *code, int LP, int L, int lane, bool reset, bool rev,
-                                           int shift, int &head)
+__device__ __forceinline__ void update_ref(WalkSmem<NW> &s, uint4 *cnt, int L, int lane, bool reset, bool rev, int shift, int &head)
 {
 	if (reset) head = 0;
 	else { head += shift; if (head >= L) head -= L; }
+	const int sh = 2 * (lane & 15);
 #pragma unroll
 	for (int t = 0; t < NW; t++) {
-		int i = lane + 32 * t;
+		const int i = lane + 32 * t;
 		u32 out = 0;
 		if (i < L) {
-			int src = rev ? L - 1 - i : i;
+			const int src = rev ? L - 1 - i : i;
 			u32 cc = (u32)(s.cur[src >> 5] >> (2 * (src & 31))) & 3u;
 			if (rev) cc ^= 3u;
-			u32 ci = ((cc & 1u) << 1) | (cc >> 1); // bit code (A0 G1 C2 T3) -> chartoint order (A0 C1 G2 T3)
 			int slot = head + i;
 			if (slot >= L) slot -= L;
-			if (reset || i >= L - shift) {
-				cnt[0 * LP + slot] = 0; cnt[1 * LP + slot] = 0; cnt[2 * LP + slot] = 0; cnt[3 * LP + slot] = 0;
-				cnt[ci * LP + slot] = 1;
-				out = cc;
-			} else {
-				cnt[ci * LP + slot] += 1;
-				u32 mx = 0, ind = 0;
-#pragma unroll
-				for (u32 k = 0; k < 4; k++) { u32 v = cnt[k * LP + slot]; if (v > mx) { mx = v; ind = k; } }
-				out = ((ind & 1u) << 1) | (ind >> 1);
-			}
-			code[i] = (u8)out;
+			// counts are kept in chartoint order A,C,G,T (reorder.cpp:139-142); the bit code is A0 G1 C2 T3
+			uint4 v = (reset || i >= L - shift) ? make_uint4(0, 0, 0, 0) : cnt[slot];
+			v.x += cc == 0; v.y += cc == 2; v.z += cc == 1; v.w += cc == 3;
+			cnt[slot] = v;
+			// argmax, ties -> A < C < G < T with strict '>' from max = 0 (reorder.cpp:893-899)
+			u32 mx = v.x;
+			if (v.y > mx) { mx = v.y; out = 2; }
+			if (v.z > mx) { mx = v.z; out = 1; }
+			if (v.w > mx) { mx = v.w; out = 3; }
 		}
-		u32 b0 = __ballot_sync(0xffffffffu, out & 1u), b1 = __ballot_sync(0xffffffffu, (out >> 1) & 1u);
-		if (lane == 0) s.ref[t] = spread32(b0) | (spread32(b1) << 1);
+		const u32 piece = out << sh;
+		const u32 lo = __reduce_or_sync(0xffffffffu, lane < 16 ? piece : 0u);
+		const u32 hi = __reduce_or_sync(0xffffffffu, lane >= 16 ? piece : 0u);
+		if (lane == 0) s.ref[t] = (u64)lo | ((u64)hi << 32);
 	}
 	__syncwarp();
-#pragma unroll
-	for (int t = 0; t < NW; t++) {
-		int i = lane + 32 * t;
-		u32 out = 0;
-		if (i < L) out = (u32)code[L - 1 - i] ^ 3u;
-		u32 b0 = __ballot_sync(0xffffffffu, out & 1u), b1 = __ballot_sync(0xffffffffu, (out >> 1) & 1u);
-		if (lane == 0) s.rref[t] = spread32(b0) | (spread32(b1) << 1);
+	if (lane < NW) {
+		const int sft = 2 * (32 * NW - L);
+		const u64 t0 = revpairs64_w(s.ref[NW - 1 - lane]);
+		const u64 t1 = lane + 1 < NW ? revpairs64_w(s.ref[NW - 2 - lane]) : 0ull;
+		const u64 r = sft ? (t0 >> sft) | (t1 << (64 - sft)) : t0;
+		s.rref[lane] = r ^ lowmask(2 * L - 64 * lane);
 	}
 	__syncwarp();
 }
@@ -388,17 +381,16 @@ __device__ __forceinline__ bool try_claim(u32 *claim, u32 rid)
 template <int NW>
 __global__ void __launch_bounds__(WALK_WARPS * 32) walk_kernel(WalkArgs a)
 {
-	extern __shared__ u64 smem_raw[];
+	extern __shared__ uint4 smem_raw[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const u32 wid = blockIdx.x * WALK_WARPS + warp;
 	if (wid >= a.walkers) return;
 	const int L = a.L, LP = (L + 31) & ~31;
 	// per-warp shared state
-	const size_t per_warp = sizeof(WalkSmem<NW>) + (size_t)16 * LP + LP;
+	const size_t per_warp = sizeof(WalkSmem<NW>) + (size_t)16 * LP;
 	char *base = reinterpret_cast<char *>(smem_raw) + per_warp * warp;
 	WalkSmem<NW> &s = *reinterpret_cast<WalkSmem<NW> *>(base);
-	u32 *cnt = reinterpret_cast<u32 *>(base + sizeof(WalkSmem<NW>));
-	u8 *code = reinterpret_cast<u8 *>(base + sizeof(WalkSmem<NW>) + (size_t)16 * LP);
+	uint4 *cnt = reinterpret_cast<uint4 *>(base + sizeof(WalkSmem<NW>));
 
 	u64 c_steps = 0, c_probes = 0, c_hits = 0, c_cmp = 0, c_fail = 0, c_restart = 0;
 
@@ -425,9 +417,12 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) walk_kernel(WalkArgs a)
 	int head = 0;
 	if (lane < NW) s.cur[lane] = __ldg(&a.reads[(size_t)current * NW + lane]);
 	__syncwarp();
-	update_ref<NW>(s, cnt, code, LP, L, lane, true, false, 0, head);
+	update_ref<NW>(s, cnt, L, lane, true, false, 0, head);
 	bool prev_unmatched = true;
 	u32 prev = current;
+	// restart state: current stripe, downward cursor inside it, stripes visited
+	u32 stripe = wid, stripes_tried = 0;
+	long long cursor = (long long)((((u64)wid + 1) * a.n) / a.walkers) - 1;
 
 	const int kind = lane & 3;          // 0: fwd dict0, 1: fwd dict1, 2: rev dict0, 3: rev dict1 (reorder.cpp:517-643 order)
 	const bool rev = kind >= 2;
@@ -455,15 +450,14 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) walk_kernel(WalkArgs a)
 			c_probes += __popc(__ballot_sync(0xffffffffu, valid));
 			c_hits += __popc(__ballot_sync(0xffffffffu, hit));
 			// candidate scan state: next index to look at (descending), live entries seen so far
-			long long idx = hit ? (long long)bstart + bsize - 1 : -1;
-			const long long lo = bstart;
+			u32 left = hit ? bsize : 0u; // entries of the bin not looked at yet (scanned from the tail, reorder.cpp:540)
 			int seen = 0;
 			u32 cand = 0xffffffffu;
 			auto advance = [&]() {
 				cand = 0xffffffffu;
-				while (idx >= lo && seen < a.maxsearch) {
-					u32 rid = __ldg(&dv.ids[idx]);
-					idx--;
+				while (left > 0 && seen < a.maxsearch) {
+					left--;
+					u32 rid = __ldg(&dv.ids[bstart + left]);
 					if (!is_unclaimed(a.claim, rid)) continue; // removed from the bin in the reference (505-514)
 					seen++;
 					u64 rw[NW];
@@ -498,7 +492,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) walk_kernel(WalkArgs a)
 			current = k_rid;
 			if (lane < NW) s.cur[lane] = __ldg(&a.reads[(size_t)current * NW + lane]);
 			__syncwarp();
-			update_ref<NW>(s, cnt, code, LP, L, lane, false, k_rev, k_j, head);
+			update_ref<NW>(s, cnt, L, lane, false, k_rev, k_j, head);
 			if (lane == 0) {
 				if (prev_unmatched) emit(mkrec(prev, (u32)L, 0, 0, 0));
 				emit(mkrec(current, (u32)k_j, (u32)k_rev, 1, 0));
@@ -506,44 +500,63 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) walk_kernel(WalkArgs a)
 			prev_unmatched = false;
 			continue;
 		}
-		// ---- no match: new chain head = highest unclaimed index (reorder.cpp:650-688).  The reference keeps a
-		// private cursor per thread; a shared monotone hint picks the same read and avoids T full scans.
+		// ---- no match: new chain head (reorder.cpp:650-688).  The reference takes the highest unclaimed index through a
+		// private downward cursor per thread.  Here the reads are cut into one stripe per walker; a walker scans its own
+		// stripe downward first and then the following stripes, so concurrent restarts do not fight over one bit.  With
+		// one walker the stripe is the whole array and the choice is exactly the reference's.
 		bool got_head = false;
-		while (true) {
-			long long p = 0;
-			if (lane == 0) p = *((volatile long long *)a.gpos);
-			p = __shfl_sync(0xffffffffu, p, 0);
-			if (p < 0) break;
-			long long topw = p >> 5;
-			long long wi = topw - lane;
-			u32 word = wi >= 0 ? *((volatile u32 *)&a.claim[wi]) : 0u;
-			if (lane == 0) { int b = (int)(p & 31); if (b != 31) word &= (2u << b) - 1u; }
-			u32 bal = __ballot_sync(0xffffffffu, word != 0u);
-			if (!bal) {
-				if (lane == 0) atomicMin(a.gpos, ((topw - 31) << 5) - 1);
+		while (stripes_tried < a.walkers) {
+			const long long slo = (long long)(((u64)stripe * a.n) / a.walkers);
+			if (cursor < slo) {
+				// stripe exhausted: everything in it is claimed for good
+				if (lane == 0) a.stripe_done[stripe] = 1u;
+				// move to the next stripe (cyclically) that is not known to be finished, 32 flags at a time
+				bool found_stripe = false;
+				while (stripes_tried + 1 < a.walkers) {
+					const u32 span = min(32u, a.walkers - 1 - stripes_tried);
+					u32 cand = stripe + 1 + lane;
+					if (cand >= a.walkers) cand -= a.walkers;
+					const bool open_ = (u32)lane < span && *((volatile u32 *)&a.stripe_done[cand]) == 0u;
+					const u32 bal = __ballot_sync(0xffffffffu, open_);
+					if (bal) {
+						const u32 f = __ffs(bal) - 1;
+						stripe = stripe + 1 + f;
+						if (stripe >= a.walkers) stripe -= a.walkers;
+						stripes_tried += f + 1;
+						found_stripe = true;
+						break;
+					}
+					stripe += span;
+					if (stripe >= a.walkers) stripe -= a.walkers;
+					stripes_tried += span;
+				}
+				if (!found_stripe) { stripes_tried = a.walkers; break; }
+				cursor = (long long)((((u64)stripe + 1) * a.n) / a.walkers) - 1;
 				continue;
 			}
+			const long long topw = cursor >> 5;
+			const long long wi = topw - lane;
+			u32 word = (wi >= 0 && wi >= (slo >> 5)) ? *((volatile u32 *)&a.claim[wi]) : 0u;
+			if (lane == 0) { int bt = (int)(cursor & 31); if (bt != 31) word &= (2u << bt) - 1u; }
+			if (wi == (slo >> 5)) word &= ~((1u << (slo & 31)) - 1u);
+			u32 bal = __ballot_sync(0xffffffffu, word != 0u);
+			if (!bal) { cursor = (topw - 31) * 32 - 1; continue; }
 			int src = __ffs(bal) - 1;
 			u32 wv = __shfl_sync(0xffffffffu, word, src);
-			long long widx = topw - src;
 			int bit = 31 - __clz(wv);
-			u32 j = (u32)(widx * 32 + bit);
+			u32 j = (u32)((topw - src) * 32 + bit);
 			int got = 0;
 			if (lane == 0) got = try_claim(a.claim, j);
 			got = __shfl_sync(0xffffffffu, got, 0);
-			if (got) {
-				if (lane == 0) atomicMin(a.gpos, (long long)j - 1);
-				current = j;
-				got_head = true;
-				break;
-			}
+			cursor = (long long)j - 1; // j is claimed now, by this walker or by another one
+			if (got) { current = j; got_head = true; break; }
 		}
 		if (lane == 0 && prev_unmatched) emit(mkrec(prev, 0, 0, 0, 1)); // previous head was a singleton (672-684)
 		if (!got_head) break;
 		c_restart++;
 		if (lane < NW) s.cur[lane] = __ldg(&a.reads[(size_t)current * NW + lane]);
 		__syncwarp();
-		update_ref<NW>(s, cnt, code, LP, L, lane, true, false, 0, head);
+		update_ref<NW>(s, cnt, L, lane, true, false, 0, head);
 		prev_unmatched = true;
 		prev = current;
 	}
@@ -617,12 +630,41 @@ template <int NW>
 static int launch_walk(harcgpu_ctx *c, const WalkArgs &a)
 {
 	int LP = (c->L + 31) & ~31;
-	size_t per_warp = sizeof(WalkSmem<NW>) + (size_t)16 * LP + LP;
+	size_t per_warp = sizeof(WalkSmem<NW>) + (size_t)16 * LP;
 	size_t smem = per_warp * WALK_WARPS;
 	CK(cudaFuncSetAttribute(walk_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	walk_kernel<NW><<<cdiv(a.walkers, WALK_WARPS), WALK_WARPS * 32, smem, c->st>>>(a);
+	walk_kernel<NW><<<KL + cdiv(a.walkers, WALK_WARPS), WALK_WARPS * 32, smem, c->st>>>(a);
 	CK(cudaGetLastError());
 	return 0;
+}
+
+// walkers that can be resident at once: a walker that is not resident only starts after the others have finished
+template <int NW>
+static int resident_warps(harcgpu_ctx *c, u32 *out)
+{
+	int LP = (c->L + 31) & ~31;
+	size_t smem = (sizeof(WalkSmem<NW>) + (size_t)16 * LP) * WALK_WARPS;
+	int nb = 0, sms = 0;
+	CK(cudaFuncSetAttribute(walk_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, walk_kernel<NW>, WALK_WARPS * 32, smem));
+	CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+	*out = (u32)nb * (u32)sms * WALK_WARPS;
+	return 0;
+}
+static int walk_resident_warps(harcgpu_ctx *c, u32 *out)
+{
+	switch (c->NW) {
+	case 1: return resident_warps<1>(c, out);
+	case 2: return resident_warps<2>(c, out);
+	case 3: return resident_warps<3>(c, out);
+	case 4: return resident_warps<4>(c, out);
+	case 5: return resident_warps<5>(c, out);
+	case 6: return resident_warps<6>(c, out);
+	case 7: return resident_warps<7>(c, out);
+	case 8: return resident_warps<8>(c, out);
+	}
+	harcgpu_set_error("unsupported read length %d", c->L);
+	return -1;
 }
 
 int s1_reorder(harcgpu_ctx *c)
@@ -640,9 +682,9 @@ int s1_reorder(harcgpu_ctx *c)
 
 	// walkers: the reference's num_thr.  Auto: one walker per 2048 reads (each extra walker costs ~4 chain
 	// heads; >= 2000-4000 reads per walker keeps the size within budget), capped at 32 resident warps per SM.
-	cudaDeviceProp prop;
-	CK(cudaGetDeviceProperties(&prop, c->device));
-	u32 walkers = c->p.walkers > 0 ? (u32)c->p.walkers : (u32)std::min<u64>((u64)prop.multiProcessorCount * 32, std::max<u64>(1, n / 2048));
+	u32 resident = 0;
+	if (walk_resident_warps(c, &resident)) return -1;
+	u32 walkers = c->p.walkers > 0 ? (u32)c->p.walkers : (u32)std::min<u64>(resident, std::max<u64>(1, n / 2048));
 	if (walkers > n) walkers = n;
 	c->walkers_used = walkers;
 
@@ -655,10 +697,11 @@ int s1_reorder(harcgpu_ctx *c)
 		return -1;
 	CK(cudaMemsetAsync(chunk_ctr, 0, 4, st));
 	CK(cudaMemsetAsync(chunk_fill, 0, 4 * (size_t)max_chunks, st));
-	init_claim_kernel<<<cdiv((n + 31) / 32, 256), 256, 0, st>>>(c->claim, n);
+	init_claim_kernel<<<KL + cdiv((n + 31) / 32, 256), 256, 0, st>>>(c->claim, n);
 	CK(cudaGetLastError());
-	long long gp = (long long)n - 1;
-	CK(cudaMemcpyAsync(c->gpos, &gp, 8, cudaMemcpyHostToDevice, st));
+	u32 *stripe_done = nullptr;
+	if (c->alloc(&stripe_done, walkers)) return -1;
+	CK(cudaMemsetAsync(stripe_done, 0, 4 * (size_t)walkers, st));
 
 	WalkArgs a;
 	a.reads = c->reads; a.n = n; a.L = c->L; a.maxmatch = c->p.maxmatch; a.thresh = c->p.thresh; a.maxsearch = c->p.maxsearch;
@@ -669,7 +712,7 @@ int s1_reorder(harcgpu_ctx *c)
 		a.d[l].dstart = c->p.dict_start[ll]; a.d[l].dend = c->p.dict_end[ll];
 		a.kbits[l] = c->d1[ll].nbits;
 	}
-	a.claim = c->claim; a.gpos = c->gpos; a.walkers = walkers;
+	a.claim = c->claim; a.stripe_done = stripe_done; a.walkers = walkers;
 	a.recs = recs; a.chunk_key = chunk_key; a.chunk_fill = chunk_fill; a.chunk_ctr = chunk_ctr; a.max_chunks = max_chunks;
 	a.counters = c->counters;
 	c->tic();
@@ -699,18 +742,18 @@ int s1_reorder(harcgpu_ctx *c)
 	    c->alloc(&cs, nchunks) || c->alloc(&om, nchunks) || c->alloc(&os, nchunks) || c->alloc(&totals, 2) ||
 	    c->alloc(&scan_tmp, scan_tmp_elems(nchunks)))
 		return -1;
-	iota_kernel<<<cdiv(nchunks, 256), 256, 0, st>>>(chunk_id, nchunks);
+	iota_kernel<<<KL + cdiv(nchunks, 256), 256, 0, st>>>(chunk_id, nchunks);
 	CK(cudaGetLastError());
 	size_t tb = 0;
 	void *cub_tmp = nullptr;
 	CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, chunk_key, key_sorted, chunk_id, chunk_sorted, (int64_t)nchunks, 0, 64, st));
 	if (c->alloc((char **)&cub_tmp, tb)) return -1;
 	CK(cub::DeviceRadixSort::SortPairs(cub_tmp, tb, chunk_key, key_sorted, chunk_id, chunk_sorted, (int64_t)nchunks, 0, 64, st));
-	chunk_count_kernel<<<cdiv((size_t)nchunks * 32, 256), 256, 0, st>>>(recs, chunk_sorted, chunk_fill, nchunks, cm, cs);
+	chunk_count_kernel<<<KL + cdiv((size_t)nchunks * 32, 256), 256, 0, st>>>(recs, chunk_sorted, chunk_fill, nchunks, cm, cs);
 	CK(cudaGetLastError());
 	if (exclusive_scan_u32(cm, om, nchunks, scan_tmp, totals, st)) return -1;
 	if (exclusive_scan_u32(cs, os, nchunks, scan_tmp, totals + 1, st)) return -1;
-	chunk_gather_kernel<<<cdiv((size_t)nchunks * 32, 256), 256, 0, st>>>(recs, chunk_sorted, chunk_fill, nchunks, om, os, c->order,
+	chunk_gather_kernel<<<KL + cdiv((size_t)nchunks * 32, 256), 256, 0, st>>>(recs, chunk_sorted, chunk_fill, nchunks, om, os, c->order,
 	                                                                      c->rev, c->flag, c->pos, c->order_s);
 	CK(cudaGetLastError());
 	u32 tot[2];
@@ -723,7 +766,7 @@ int s1_reorder(harcgpu_ctx *c)
 	if ((u64)tot[0] + tot[1] != n) { harcgpu_set_error("reorder lost reads: %u matched + %u singletons != %u", tot[0], tot[1], n); return -1; }
 	c->release(recs); c->release(chunk_key); c->release(key_sorted); c->release(chunk_fill); c->release(chunk_ctr);
 	c->release(chunk_id); c->release(chunk_sorted); c->release(cm); c->release(cs); c->release(om); c->release(os);
-	c->release(totals); c->release(scan_tmp); c->release(cub_tmp);
+	c->release(totals); c->release(scan_tmp); c->release(cub_tmp); c->release(stripe_done);
 	c->reordered = true;
 	return 0;
 }

@@ -514,7 +514,7 @@ int s2_set_stream_from_stage1(harcgpu_ctx *c)
 	    c->alloc(&c->s_pos, m))
 		return -1;
 	if (m) {
-		DISPATCH_NW(c->NW, (gather_stream_kernel<NW><<<cdiv(m, 128), 128, 0, st>>>(c->reads, c->order, c->rev, m, c->L, c->sreads)));
+		DISPATCH_NW(c->NW, (gather_stream_kernel<NW><<<KL + cdiv(m, 128), 128, 0, st>>>(c->reads, c->order, c->rev, m, c->L, c->sreads)));
 		CK(cudaGetLastError());
 		CK(cudaMemcpyAsync(c->s_order, c->order, 4 * (size_t)m, cudaMemcpyDeviceToDevice, st));
 		CK(cudaMemcpyAsync(c->s_rev, c->rev, m, cudaMemcpyDeviceToDevice, st));
@@ -550,8 +550,8 @@ int s2_set_stream_host(harcgpu_ctx *c, const char *dna, const char *flag, const 
 	return 0;
 }
 
-// encoder.cpp:823-872 + 132-148
-int s2_load_pool(harcgpu_ctx *c, const char *s_ascii, const u32 *order_s, u32 n_s, const char *N_ascii, u32 n_N)
+// encoder.cpp:823-872 + 132-148.  d_N: device buffer with the N reads (16-byte aligned) or null; h_N: host buffer or null.
+static int load_pool_impl(harcgpu_ctx *c, const char *s_ascii, const u32 *order_s, u32 n_s, const char *h_N, const void *d_N, u32 n_N)
 {
 	free_pool(c);
 	cudaStream_t st = c->st;
@@ -567,7 +567,7 @@ int s2_load_pool(harcgpu_ctx *c, const char *s_ascii, const u32 *order_s, u32 n_
 	const size_t line = (size_t)c->L + 1;
 	if (n_s) {
 		if (from_stage1) {
-			DISPATCH_NW(c->NW, (gather_stream_kernel<NW><<<cdiv(n_s, 128), 128, 0, st>>>(c->reads, c->order_s, nullptr, n_s, c->L, c->pool)));
+			DISPATCH_NW(c->NW, (gather_stream_kernel<NW><<<KL + cdiv(n_s, 128), 128, 0, st>>>(c->reads, c->order_s, nullptr, n_s, c->L, c->pool)));
 			CK(cudaGetLastError());
 			CK(cudaMemcpyAsync(c->pool_order, c->order_s, 4 * (size_t)n_s, cudaMemcpyDeviceToDevice, st));
 		} else {
@@ -582,24 +582,32 @@ int s2_load_pool(harcgpu_ctx *c, const char *s_ascii, const u32 *order_s, u32 n_
 	}
 	if (n_N) {
 		char *d = nullptr;
-		if (c->alloc(&d, n_N * line + 16)) return -1;
-		CK(cudaMemcpyAsync(d, N_ascii, n_N * line, cudaMemcpyHostToDevice, st));
-		if (s1_packN(c, d, n_N, c->pool + (size_t)n_s * c->NW, c->poolN + (size_t)n_s * c->NW)) return -1;
-		iota_off_kernel<<<cdiv(n_N, 256), 256, 0, st>>>(c->pool_order + n_s, n_N); // order_s[i] = i - numreads_s (869-870)
+		if (!d_N) {
+			if (c->alloc(&d, n_N * line + 16)) return -1;
+			CK(cudaMemcpyAsync(d, h_N, n_N * line, cudaMemcpyHostToDevice, st));
+		}
+		if (s1_packN(c, d_N ? d_N : d, n_N, c->pool + (size_t)n_s * c->NW, c->poolN + (size_t)n_s * c->NW)) return -1;
+		iota_off_kernel<<<KL + cdiv(n_N, 256), 256, 0, st>>>(c->pool_order + n_s, n_N); // order_s[i] = i - numreads_s (869-870)
 		CK(cudaGetLastError());
-		CK(cudaStreamSynchronize(st));
-		c->release(d);
+		if (d) { CK(cudaStreamSynchronize(st)); c->release(d); }
 	}
 	// dictionary windows of encoder.cpp:132-145
 	int ds[2], de[2];
 	const int L = c->L;
 	if (L > 50) { ds[0] = 0; de[0] = 20; ds[1] = 21; de[1] = 41; }
 	else { ds[0] = 0; de[0] = 20 * L / 50; ds[1] = 20 * L / 50 + 1; de[1] = 41 * L / 50; }
+	c->tic();
 	for (int l = 0; l < 2; l++)
 		if (build_dict(c, c->d2[l], c->pool, c->poolN, P, c->NW, ds[l], de[l], 3)) return -1;
+	c->toc("pooldict");
 	c->pool_set = true;
 	return 0;
 }
+int s2_load_pool(harcgpu_ctx *c, const char *s_ascii, const u32 *order_s, u32 n_s, const char *N_ascii, u32 n_N)
+{
+	return load_pool_impl(c, s_ascii, order_s, n_s, N_ascii, nullptr, n_N);
+}
+int s2_load_pool_dev(harcgpu_ctx *c, const void *d_N_ascii, u32 n_N) { return load_pool_impl(c, nullptr, nullptr, 0, nullptr, d_N_ascii, n_N); }
 
 int s2_encode(harcgpu_ctx *c)
 {
@@ -630,13 +638,13 @@ int s2_encode(harcgpu_ctx *c)
 	}
 	if (c->alloc(&scan_tmp, scan_tmp_elems(2 * scan_n + 64))) return -1;
 	if (m) {
-		natstart_kernel<<<cdiv(m, 256), 256, 0, st>>>(c->s_flag, m, per, ns);
+		natstart_kernel<<<KL + cdiv(m, 256), 256, 0, st>>>(c->s_flag, m, per, ns);
 		if (exclusive_scan_u32(ns, ex, m, scan_tmp, nullptr, st)) return -1;
-		scatter_idx_kernel<<<cdiv(m, 256), 256, 0, st>>>(ns, ex, m, nat_idx);
-		cstart_kernel<<<cdiv(m, 256), 256, 0, st>>>(ns, ex, nat_idx, c->s_pos, m, L, cs, inc);
+		scatter_idx_kernel<<<KL + cdiv(m, 256), 256, 0, st>>>(ns, ex, m, nat_idx);
+		cstart_kernel<<<KL + cdiv(m, 256), 256, 0, st>>>(ns, ex, nat_idx, c->s_pos, m, L, cs, inc);
 		if (exclusive_scan_u32(cs, ex, m, scan_tmp, d_tot32, st)) return -1;
 		if (exclusive_scan_u64(inc, G, m, scan_tmp, d_tot64, st)) return -1;
-		finish_layout_kernel<<<cdiv(m, 256), 256, 0, st>>>(cs, ex, inc, G, m, cid, cstart);
+		finish_layout_kernel<<<KL + cdiv(m, 256), 256, 0, st>>>(cs, ex, inc, G, m, cid, cstart);
 		CK(cudaGetLastError());
 		u64 tot = 0;
 		CK(cudaMemcpyAsync(&NC, d_tot32, 4, cudaMemcpyDeviceToHost, st));
@@ -648,7 +656,7 @@ int s2_encode(harcgpu_ctx *c)
 	if (c->alloc(&cons2, cwords + 2)) return -1;
 	CK(cudaMemsetAsync(cons2 + cwords, 0, 16, st));
 	if (m) {
-		consensus_kernel<<<cdiv(cwords * 32, 256), 256, 0, st>>>(G, c->sreads, m, L, NWv, TOT, cons2);
+		consensus_kernel<<<KL + cdiv(cwords * 32, 256), 256, 0, st>>>(G, c->sreads, m, L, NWv, TOT, cons2);
 		CK(cudaGetLastError());
 	}
 
@@ -658,7 +666,7 @@ int s2_encode(harcgpu_ctx *c)
 	u32 M = 0;
 	if (c->alloc(&best, P)) return -1;
 	if (P) {
-		fill64_kernel<<<cdiv(P, 256), 256, 0, st>>>(best, P, NOBEST);
+		fill64_kernel<<<KL + cdiv(P, 256), 256, 0, st>>>(best, P, NOBEST);
 		CK(cudaGetLastError());
 	}
 	if (P && m && TOT >= (u64)L) {
@@ -671,12 +679,12 @@ int s2_encode(harcgpu_ctx *c)
 		}
 		a.L = L; a.thresh_s = c->p.thresh_s; a.maxsearch = c->p.maxsearch; a.best = best;
 		u64 nwin = TOT - L + 1;
-		DISPATCH_NW(NWv, (pool_probe_kernel<NW><<<cdiv(nwin, 128), 128, 0, st>>>(a)));
+		DISPATCH_NW(NWv, (pool_probe_kernel<NW><<<KL + cdiv(nwin, 128), 128, 0, st>>>(a)));
 		CK(cudaGetLastError());
 		if (c->alloc(&af, P) || c->alloc(&exa, P) || c->alloc(&prio_u, P) || c->alloc(&rid_u, P)) return -1;
-		aligned_flag_kernel<<<cdiv(P, 256), 256, 0, st>>>(best, P, af);
+		aligned_flag_kernel<<<KL + cdiv(P, 256), 256, 0, st>>>(best, P, af);
 		if (exclusive_scan_u32(af, exa, P, scan_tmp, d_tot32, st)) return -1;
-		aligned_compact_kernel<<<cdiv(P, 256), 256, 0, st>>>(best, af, exa, P, prio_u, rid_u);
+		aligned_compact_kernel<<<KL + cdiv(P, 256), 256, 0, st>>>(best, af, exa, P, prio_u, rid_u);
 		CK(cudaGetLastError());
 		CK(cudaMemcpyAsync(&M, d_tot32, 4, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
@@ -708,11 +716,11 @@ int s2_encode(harcgpu_ctx *c)
 	u64 NB = 0;
 	u32 FN = 0;
 	if (m) {
-		place_orig_kernel<<<cdiv(m, 256), 256, 0, st>>>(G, m, iprio, M, f_src, f_kind, f_col);
+		place_orig_kernel<<<KL + cdiv(m, 256), 256, 0, st>>>(G, m, iprio, M, f_src, f_kind, f_col);
 		CK(cudaGetLastError());
 	}
 	if (M) {
-		place_ins_kernel<<<cdiv(M, 256), 256, 0, st>>>(G, m, iprio, irid, M, f_src, f_kind, f_col);
+		place_ins_kernel<<<KL + cdiv(M, 256), 256, 0, st>>>(G, m, iprio, irid, M, f_src, f_kind, f_col);
 		CK(cudaGetLastError());
 	}
 	EmitArgs ea;
@@ -721,7 +729,7 @@ int s2_encode(harcgpu_ctx *c)
 	ea.nm1 = nm1; ea.posb = posb; ea.revc = revc; ea.isN = isN; ea.ordv = ordv; ea.noff = noff; ea.exN = exN;
 	ea.noise = nullptr; ea.noisepos = nullptr; ea.o_order = nullptr; ea.o_order_N = nullptr;
 	if (F) {
-		DISPATCH_NW(NWv, (emit_count_kernel<NW><<<cdiv(F, 128), 128, 0, st>>>(ea)));
+		DISPATCH_NW(NWv, (emit_count_kernel<NW><<<KL + cdiv(F, 128), 128, 0, st>>>(ea)));
 		CK(cudaGetLastError());
 		if (exclusive_scan_u64(nm1, noff, F, scan_tmp, d_tot64, st)) return -1;
 		if (exclusive_scan_u32(isN, exN, F, scan_tmp, d_tot32, st)) return -1;
@@ -737,7 +745,7 @@ int s2_encode(harcgpu_ctx *c)
 	u32 U = 0, U_s = 0;
 	if (c->alloc(&uf, P) || c->alloc(&exU, (size_t)P + 1) || c->alloc(&ulist, P)) return -1;
 	if (P) {
-		unaligned_flag_kernel<<<cdiv(P, 256), 256, 0, st>>>(best, P, uf);
+		unaligned_flag_kernel<<<KL + cdiv(P, 256), 256, 0, st>>>(best, P, uf);
 		if (exclusive_scan_u32(uf, exU, P, scan_tmp, d_tot32, st)) return -1;
 		CK(cudaMemcpyAsync(exU + P, d_tot32, 4, cudaMemcpyDeviceToDevice, st));
 		CK(cudaMemcpyAsync(&U, d_tot32, 4, cudaMemcpyDeviceToHost, st));
@@ -751,7 +759,7 @@ int s2_encode(harcgpu_ctx *c)
 		return -1;
 	if (F) {
 		ea.noise = noise; ea.noisepos = noisepos; ea.o_order = c->o_order; ea.o_order_N = c->o_order_N;
-		DISPATCH_NW(NWv, (emit_write_kernel<NW><<<cdiv(F, 128), 128, 0, st>>>(ea)));
+		DISPATCH_NW(NWv, (emit_write_kernel<NW><<<KL + cdiv(F, 128), 128, 0, st>>>(ea)));
 		CK(cudaGetLastError());
 	}
 	const u64 sbases = (u64)U_s * L, sbytes = sbases / 4, stail = sbases % 4;
@@ -760,14 +768,14 @@ int s2_encode(harcgpu_ctx *c)
 	if (c->alloc(&c->o_single, sbytes) || c->alloc(&c->o_inputN, nbytesN) || c->alloc(&d_tail, 16 * (size_t)(K + 1))) return -1;
 	CK(cudaMemsetAsync(d_tail, 0, 16 * (size_t)(K + 1), st));
 	if (P) {
-		unaligned_kernel<<<cdiv(P, 256), 256, 0, st>>>(uf, exU, P, n_s, U_s, c->pool_order, ulist, c->o_order + Fc, c->o_order_N + FN);
+		unaligned_kernel<<<KL + cdiv(P, 256), 256, 0, st>>>(uf, exU, P, n_s, U_s, c->pool_order, ulist, c->o_order + Fc, c->o_order_N + FN);
 		CK(cudaGetLastError());
 		if (sbases) {
-			pack_singleton_kernel<<<cdiv(sbytes + 1, 256), 256, 0, st>>>(c->pool, ulist, L, NWv, sbases, sbytes, c->o_single, d_tail + 16 * (size_t)K);
+			pack_singleton_kernel<<<KL + cdiv(sbytes + 1, 256), 256, 0, st>>>(c->pool, ulist, L, NWv, sbases, sbytes, c->o_single, d_tail + 16 * (size_t)K);
 			CK(cudaGetLastError());
 		}
 		if (nbytesN) {
-			unaligned_N_kernel<<<cdiv(nbytesN, 256), 256, 0, st>>>(c->pool, c->poolN, ulist + U_s, L, NWv, nbytesN, c->o_inputN);
+			unaligned_N_kernel<<<KL + cdiv(nbytesN, 256), 256, 0, st>>>(c->pool, c->poolN, ulist + U_s, L, NWv, nbytesN, c->o_inputN);
 			CK(cudaGetLastError());
 		}
 	}
@@ -809,9 +817,9 @@ int s2_encode(harcgpu_ctx *c)
 		s.seq_bytes = ncol / 4; s.seq_ntail = (u32)(ncol % 4);
 		s.rev_bytes = cnt / 8; s.rev_ntail = (u32)(cnt % 8);
 		if (c->alloc(&s.seq, s.seq_bytes) || c->alloc(&s.rev, s.rev_bytes)) return -1;
-		if (s.seq_bytes) pack_seq_kernel<<<cdiv(s.seq_bytes, 256), 256, 0, st>>>(cons2, col0, s.seq_bytes, s.seq);
-		if (s.rev_bytes) pack_rev_kernel<<<cdiv(s.rev_bytes, 256), 256, 0, st>>>(revc, e0, s.rev_bytes, s.rev);
-		if (s.seq_ntail || s.rev_ntail) tails_kernel<<<1, 32, 0, st>>>(cons2, col1, s.seq_ntail, revc, e1, s.rev_ntail, d_tail + 16 * (size_t)k);
+		if (s.seq_bytes) pack_seq_kernel<<<KL + cdiv(s.seq_bytes, 256), 256, 0, st>>>(cons2, col0, s.seq_bytes, s.seq);
+		if (s.rev_bytes) pack_rev_kernel<<<KL + cdiv(s.rev_bytes, 256), 256, 0, st>>>(revc, e0, s.rev_bytes, s.rev);
+		if (s.seq_ntail || s.rev_ntail) tails_kernel<<<KL + 1, 32, 0, st>>>(cons2, col1, s.seq_ntail, revc, e1, s.rev_ntail, d_tail + 16 * (size_t)k);
 		CK(cudaGetLastError());
 	}
 	std::vector<char> h_tail(16 * (size_t)(K + 1));

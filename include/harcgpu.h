@@ -69,6 +69,8 @@ int harcgpu_default_params(int readlen, harcgpu_params *p);
 int harcgpu_create(int device, const harcgpu_params *p, harcgpu_ctx **out);
 void harcgpu_destroy(harcgpu_ctx *ctx);
 const char *harcgpu_last_error(void);
+/* Number of kernels this library has launched in this process (its own kernels; CUB sort passes not counted). */
+uint64_t harcgpu_launch_count(void);
 int harcgpu_device_count(void);
 
 /* ---- stage I (reorder.cpp) ------------------------------------------------------------------------------ */
@@ -104,6 +106,9 @@ int harcgpu_set_stream(harcgpu_ctx *ctx, const char *temp_dna, const char *flag,
  * after harcgpu_reorder() on the same context (the singletons are then taken from the device). */
 int harcgpu_load_pool(harcgpu_ctx *ctx, const char *singleton_ascii, const uint32_t *order_s, uint32_t n_s,
                       const char *N_ascii, uint32_t n_N);
+/* Same with the N reads already resident in device memory (16-byte aligned) and the singletons taken from
+ * harcgpu_reorder() on this context (bench: the kernel-only figure). */
+int harcgpu_load_pool_device(harcgpu_ctx *ctx, const void *d_N_ascii, uint32_t n_N);
 /* encoder.cpp:154-510 encode() + 512-616 packbits() + 619-717 buildcontig/writecontig. */
 int harcgpu_encode(harcgpu_ctx *ctx);
 int harcgpu_get_encode_sizes(harcgpu_ctx *ctx, harcgpu_encode_sizes *s);
