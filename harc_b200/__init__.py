@@ -225,24 +225,25 @@ class HarcGpu:
         self._ck(self.lib.harcgpu_get_encode_sizes(self.h, ctypes.byref(s)))
         return s
 
-    def get_set(self, k):
+    def get_set(self, k, empty=np.empty):
+        """File set k as host arrays.  `empty(n, dtype)` supplies the host buffers (e.g. views of pinned memory)."""
         z = SetSizes()
         self._ck(self.lib.harcgpu_get_set_sizes(self.h, k, ctypes.byref(z)))
-        o = dict(seq=np.empty(z.seq_bytes, np.uint8), seq_tail=np.zeros(8, np.uint8), pos=np.empty(z.pos_bytes, np.uint8),
-                 noise=np.empty(z.noise_bytes, np.uint8), noisepos=np.empty(z.noisepos_bytes, np.uint8),
-                 rev=np.empty(z.rev_bytes, np.uint8), rev_tail=np.zeros(8, np.uint8))
+        o = dict(seq=empty(z.seq_bytes, np.uint8), seq_tail=np.zeros(8, np.uint8), pos=empty(z.pos_bytes, np.uint8),
+                 noise=empty(z.noise_bytes, np.uint8), noisepos=empty(z.noisepos_bytes, np.uint8),
+                 rev=empty(z.rev_bytes, np.uint8), rev_tail=np.zeros(8, np.uint8))
         self._ck(self.lib.harcgpu_get_set(self.h, k, _ptr(o["seq"]), _ptr(o["seq_tail"]), _ptr(o["pos"]), _ptr(o["noise"]),
                                           _ptr(o["noisepos"]), _ptr(o["rev"]), _ptr(o["rev_tail"])))
         o["seq_tail"] = o["seq_tail"][: z.seq_tail]
         o["rev_tail"] = o["rev_tail"][: z.rev_tail]
         return o
 
-    def get_globals(self):
+    def get_globals(self, empty=np.empty):
         s = EncodeSizes()
         self._ck(self.lib.harcgpu_get_encode_sizes(self.h, ctypes.byref(s)))
-        o = dict(order=np.empty(s.n_order, np.uint32), order_N=np.empty(s.n_order_N, np.uint32),
-                 singleton=np.empty(s.singleton_bytes, np.uint8), singleton_tail=np.zeros(8, np.uint8),
-                 input_N=np.empty(s.input_N_bytes, np.uint8))
+        o = dict(order=empty(s.n_order, np.uint32), order_N=empty(s.n_order_N, np.uint32),
+                 singleton=empty(s.singleton_bytes, np.uint8), singleton_tail=np.zeros(8, np.uint8),
+                 input_N=empty(s.input_N_bytes, np.uint8))
         self._ck(self.lib.harcgpu_get_globals(self.h, _ptr(o["order"]), _ptr(o["order_N"]), _ptr(o["singleton"]),
                                               _ptr(o["singleton_tail"]), _ptr(o["input_N"])))
         o["singleton_tail"] = o["singleton_tail"][: s.singleton_tail]

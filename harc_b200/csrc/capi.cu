@@ -74,12 +74,6 @@ int harcgpu_create(int device, const harcgpu_params *p, harcgpu_ctx **out)
 	c->NW3 = (3 * c->L + 63) / 64;
 	memset(&c->esz, 0, sizeof c->esz);
 	CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-	{
-		cudaMemPool_t pool;
-		CK(cudaDeviceGetDefaultMemPool(&pool, device));
-		unsigned long long keep = ~0ull; // keep freed blocks cached in the pool between passes
-		CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-	}
 	CK(cudaEventCreate(&c->ev0));
 	CK(cudaEventCreate(&c->ev1));
 	if (c->alloc(&c->counters, 8) || c->alloc(&c->gpos, 1)) return -1;
@@ -93,8 +87,8 @@ void harcgpu_destroy(harcgpu_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->st);
-	for (void *q : c->allocs) cudaFreeAsync(q, c->st);
-	cudaStreamSynchronize(c->st);
+	for (auto &b : c->live) cudaFree(b.p);
+	c->trim();
 	cudaEventDestroy(c->ev0);
 	cudaEventDestroy(c->ev1);
 	cudaStreamDestroy(c->st);

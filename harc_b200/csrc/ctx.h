@@ -22,7 +22,6 @@ struct harcgpu_ctx {
 	harcgpu_params p;
 	cudaStream_t st = nullptr;
 	int L = 0, NW = 0, NW3 = 0;
-	std::vector<void *> allocs;
 	std::map<std::string, double> ms;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
@@ -62,28 +61,71 @@ struct harcgpu_ctx {
 	u8 *o_single = nullptr; char single_tail[4];
 	char *o_inputN = nullptr;
 
-	// Stream-ordered allocations from the device's default pool (release threshold raised in harcgpu_create), so the
-	// many short-lived work buffers of a pass cost no cudaMalloc/cudaFree round trips after the first pass.
+	// Device memory: a caching allocator private to the context.  Every kernel and copy of a context runs on its one
+	// stream, so a block can be handed out again as soon as it is released (reuse is stream-ordered by construction).
+	// A request takes the smallest cached block that is large enough but at most 25 % (+2 MiB) larger; otherwise it
+	// goes to cudaMalloc.  A pass repeats the sizes of the pass before it, so after the first pass no allocation
+	// reaches the driver.  (cudaMallocAsync was measured here to spend hundreds of ms per pass remapping its pool when
+	// block sizes vary between calls.)
+	struct Block { void *p; size_t bytes; };
+	std::vector<Block> live, cached;
+	size_t cached_bytes = 0, live_bytes = 0, peak_bytes = 0;
+	static size_t round_bytes(size_t b) { return b <= (1u << 20) ? (b + 511) / 512 * 512 : (b + (2u << 20) - 1) / (2u << 20) * (2u << 20); }
+	void trim()
+	{
+		for (auto &b : cached) cudaFree(b.p);
+		cached.clear();
+		cached_bytes = 0;
+	}
 	template <typename T> int alloc(T **out, size_t count)
 	{
-		void *q = nullptr;
-		size_t bytes = (count ? count : 1) * sizeof(T);
-		cudaError_t e = cudaMallocAsync(&q, bytes, st);
-		if (e != cudaSuccess) {
-			harcgpu_set_error("cudaMallocAsync(%zu bytes): %s", bytes, cudaGetErrorString(e));
-			*out = nullptr;
-			return -1;
+		size_t bytes = round_bytes((count ? count : 1) * sizeof(T));
+		size_t best = (size_t)-1;
+		for (size_t i = 0; i < cached.size(); i++)
+			if (cached[i].bytes >= bytes && cached[i].bytes <= bytes + bytes / 4 + (2u << 20) &&
+			    (best == (size_t)-1 || cached[i].bytes < cached[best].bytes))
+				best = i;
+		Block b;
+		if (best != (size_t)-1) {
+			b = cached[best];
+			cached[best] = cached.back();
+			cached.pop_back();
+			cached_bytes -= b.bytes;
+		} else {
+			void *q = nullptr;
+			cudaError_t e = cudaMalloc(&q, bytes);
+			if (e != cudaSuccess) { // give the cached blocks back to the driver and try once more
+				cudaGetLastError();
+				cudaStreamSynchronize(st);
+				trim();
+				e = cudaMalloc(&q, bytes);
+			}
+			if (e != cudaSuccess) {
+				cudaGetLastError();
+				harcgpu_set_error("cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+				*out = nullptr;
+				return -1;
+			}
+			b.p = q; b.bytes = bytes;
 		}
-		allocs.push_back(q);
-		*out = (T *)q;
+		live.push_back(b);
+		live_bytes += b.bytes;
+		if (live_bytes > peak_bytes) peak_bytes = live_bytes;
+		*out = (T *)b.p;
 		return 0;
 	}
 	void release(void *q)
 	{
 		if (!q) return;
-		for (size_t i = 0; i < allocs.size(); i++)
-			if (allocs[i] == q) { allocs[i] = allocs.back(); allocs.pop_back(); break; }
-		cudaFreeAsync(q, st);
+		for (size_t i = 0; i < live.size(); i++)
+			if (live[i].p == q) {
+				cached.push_back(live[i]);
+				cached_bytes += live[i].bytes;
+				live_bytes -= live[i].bytes;
+				live[i] = live.back();
+				live.pop_back();
+				return;
+			}
 	}
 	void tic() { cudaEventRecord(ev0, st); }
 	void toc(const char *phase)
