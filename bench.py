@@ -145,6 +145,8 @@ def main():
     ap.add_argument("--ref-reads", type=float, default=3.5e6)
     ap.add_argument("--walkers", type=int, default=0)
     ap.add_argument("--file-sets", type=int, default=1)
+    ap.add_argument("--reads-per-walker", type=int, default=0)
+    ap.add_argument("--extend", type=int, default=0)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer pass")
@@ -184,7 +186,8 @@ def main():
     torch.cuda.synchronize()
     del w["all"]
 
-    ctx = harc_b200.HarcGpu(L, device=local, walkers=args.walkers, file_sets=args.file_sets)
+    ctx = harc_b200.HarcGpu(L, device=local, walkers=args.walkers, file_sets=args.file_sets,
+                            reads_per_walker=args.reads_per_walker, extend=args.extend)
     stream = torch.cuda.ExternalStream(ctx.stream())
     phases = ["pack", "dict", "walk", "finalize", "pooldict", "encode"]
 
@@ -311,7 +314,7 @@ def main():
         "stage1": {"matched": m, "singletons": s, "chain_heads": u, "probes_per_read": cnt["probes"] / max(1, cnt["steps"]),
                    "compares_per_read": cnt["compares"] / max(1, cnt["steps"]), "claim_fails": cnt["claim_fails"]},
         "stage2": {"aligned_singletons": es.aligned_singletons, "aligned_N": es.aligned_N},
-        "roofline": {"bound": "hbm", "kernel": "walk_kernel<4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "walk_kernel<4> (8 lanes per walker)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,
                      "algorithmic_bytes_per_clean_read": balg, "model_probes_per_read": P,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},

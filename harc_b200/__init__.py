@@ -26,7 +26,8 @@ class Params(ctypes.Structure):
     """harcgpu_params: the macros of the reference's generated src/config.h (harc:52-63) + walkers/file_sets."""
     _fields_ = [("readlen", ctypes.c_int), ("maxmatch", ctypes.c_int), ("thresh", ctypes.c_int), ("thresh_s", ctypes.c_int),
                 ("numdict", ctypes.c_int), ("maxsearch", ctypes.c_int), ("dict_start", ctypes.c_int * 2),
-                ("dict_end", ctypes.c_int * 2), ("walkers", ctypes.c_int), ("file_sets", ctypes.c_int)]
+                ("dict_end", ctypes.c_int * 2), ("walkers", ctypes.c_int), ("file_sets", ctypes.c_int),
+                ("reads_per_walker", ctypes.c_int), ("extend", ctypes.c_int), ("lanes_per_walker", ctypes.c_int)]
 
 
 class EncodeSizes(ctypes.Structure):
@@ -98,13 +99,16 @@ class HarcError(RuntimeError):
     pass
 
 
-def default_params(readlen, walkers=0, file_sets=1):
+def default_params(readlen, walkers=0, file_sets=1, reads_per_walker=0, extend=0, lanes_per_walker=0):
     lib = load_library()
     p = Params()
     if lib.harcgpu_default_params(int(readlen), ctypes.byref(p)):
         raise HarcError(lib.harcgpu_last_error().decode())
     p.walkers = walkers
     p.file_sets = file_sets
+    p.reads_per_walker = reads_per_walker
+    p.extend = extend
+    p.lanes_per_walker = lanes_per_walker
     return p
 
 
@@ -122,9 +126,10 @@ def _ptr(a):
 class HarcGpu:
     """One context on one GPU.  Method names follow include/harcgpu.h."""
 
-    def __init__(self, readlen=None, device=0, params=None, walkers=0, file_sets=1):
+    def __init__(self, readlen=None, device=0, params=None, walkers=0, file_sets=1, reads_per_walker=0, extend=0,
+                 lanes_per_walker=0):
         self.lib = load_library()
-        self.p = params if params is not None else default_params(readlen, walkers, file_sets)
+        self.p = params if params is not None else default_params(readlen, walkers, file_sets, reads_per_walker, extend, lanes_per_walker)
         self.L = self.p.readlen
         h = ctypes.c_void_p()
         self._ck(self.lib.harcgpu_create(device, ctypes.byref(self.p), ctypes.byref(h)))

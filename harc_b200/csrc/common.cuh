@@ -40,17 +40,18 @@ __device__ __forceinline__ u64 getbits(const u64 *w, int words, int pos, int n)
 // mask with the low `n` bits set, n clamped to [0,64]
 __device__ __forceinline__ u64 lowmask(int n) { return n >= 64 ? ~0ull : (n <= 0 ? 0ull : ((1ull << n) - 1)); }
 
-// splitmix64 finaliser: slot hash of the key-storing table that stands in for BooPHF (BooPHF.h:970-1008)
-__device__ __forceinline__ u64 mix64(u64 x)
+// Slot hash of the key-storing table that stands in for BooPHF (BooPHF.h:970-1008): one 64-bit multiply, the high
+// half (the well-mixed one) folded with the low half.
+__device__ __forceinline__ u32 slot_hash(u64 x)
 {
-	x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
-	x ^= x >> 27; x *= 0x94d049bb133111ebull;
-	x ^= x >> 31;
-	return x;
+	x *= 0x9E3779B97F4A7C15ull;
+	return (u32)(x >> 32) ^ (u32)x;
 }
 
 // One dictionary: canonical CSR (keys ascending, ids ascending inside a bin: reorder.cpp:344-391) plus an
-// open-addressing table key -> (bin start, bin size).  A slot is 16 bytes {key, start | size<<32}; size==0 = empty.
+// open-addressing table key -> bin.  A slot is 16 bytes {key, val}: val == 0 = empty, else size = val >> 32 and the low
+// half is the bin's first index into ids[] -- or, for a bin of one read (most bins), the read id itself, so that the
+// common probe needs no second dependent load.
 struct DictDev {
 	u64 *keys = nullptr;      // [numkeys] ascending
 	u32 *start = nullptr;     // [numkeys+1]
@@ -67,16 +68,30 @@ struct DictView {
 	int dstart, dend; // in bases
 };
 
-__device__ __forceinline__ bool dict_lookup(const DictView &d, u64 key, u32 &start, u32 &size)
+// Slots are probed in buckets of two (one 32-byte sector): a key hashes to an even slot and is inserted into the first
+// empty slot from there on, so a lookup reads both slots of a bucket at once and stops at the first empty one.
+// true if the key is present: size = reads in the bin, lo = first index into ids[] (size > 1) or the read id (size == 1)
+__device__ __forceinline__ bool dict_resolve(const DictView &d, u64 key, u32 h, ulonglong2 s0, ulonglong2 s1, u32 &lo, u32 &size)
 {
-	u32 h = (u32)mix64(key) & d.slot_mask;
 	while (true) {
-		ulonglong2 s = __ldg(&d.slots[h]);
-		u32 sz = (u32)(s.y >> 32);
-		if (sz == 0) return false;
-		if (s.x == key) { start = (u32)s.y; size = sz; return true; }
-		h = (h + 1) & d.slot_mask;
+		if ((u32)(s0.y >> 32) == 0u) return false;
+		if (s0.x == key) { lo = (u32)s0.y; size = (u32)(s0.y >> 32); return true; }
+		if ((u32)(s1.y >> 32) == 0u) return false;
+		if (s1.x == key) { lo = (u32)s1.y; size = (u32)(s1.y >> 32); return true; }
+		h = (h + 2) & d.slot_mask;
+		s0 = __ldg(&d.slots[h]);
+		s1 = __ldg(&d.slots[h + 1]);
 	}
+}
+__device__ __forceinline__ bool dict_lookup(const DictView &d, u64 key, u32 &lo, u32 &size)
+{
+	const u32 h = slot_hash(key) & d.slot_mask & ~1u;
+	return dict_resolve(d, key, h, __ldg(&d.slots[h]), __ldg(&d.slots[h + 1]), lo, size);
+}
+// entry t (0 = lowest id) of a bin returned by dict_lookup
+__device__ __forceinline__ u32 bin_entry(const DictView &d, u32 lo, u32 size, u32 t)
+{
+	return size == 1 ? lo : __ldg(&d.ids[lo + t]);
 }
 
 // ---- hand-written device-wide exclusive scan (scan.cu) ------------------------------------------------------

@@ -225,9 +225,9 @@ __global__ void __launch_bounds__(128) pool_probe_kernel(PoolArgs a)
 			for (int k = 0; k < NW; k++) rc[k] = t[k] ^ lowmask(2 * L - 64 * k);
 			have_rc = true;
 		}
-		long long end = (long long)bstart + bsize, lo = max((long long)bstart, end - a.maxsearch);
-		for (long long t = end - 1; t >= lo; t--) { // no break: every read of the bin within thresh_s is taken (293-317)
-			u32 rid = __ldg(&dv.ids[t]);
+		const u32 tlo = bsize > (u32)a.maxsearch ? bsize - (u32)a.maxsearch : 0u;
+		for (u32 t = bsize; t-- > tlo;) { // from the tail, no break: every read of the bin within thresh_s is taken (293-317)
+			const u32 rid = bin_entry(dv, bstart, bsize, t);
 			const u64 *p2 = a.pool + (size_t)rid * NW, *pn = a.poolN + (size_t)rid * NW;
 			int d = 0;
 #pragma unroll

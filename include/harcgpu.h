@@ -34,6 +34,10 @@ typedef struct {
 	int dict_end[2];   /* harc:58,60 */
 	int walkers;       /* concurrent chain walkers = the reference's num_thr in reorder.cpp:455; 0 = choose for the GPU */
 	int file_sets;     /* K, number of read_*.txt.<k> output sets = the reference's num_thr in encoder.cpp:169-196; 0 -> 1 */
+	int reads_per_walker; /* walkers == 0: one walker per this many reads, capped at what the GPU keeps resident; 0 -> 4096 */
+	int extend;        /* left extension of new chains (not in the reference; same file format): 1 on, -1 off,
+	                      0 = on when more than one walker runs (one walker without it = the reference at num_thr=1) */
+	int lanes_per_walker; /* GPU lanes that cooperate on one walker: 8, 16 or 32; 0 = default */
 } harcgpu_params;
 
 /* Sizes of everything stage II produced, so the caller can allocate before harcgpu_get_*.  (encoder.cpp:457-508) */

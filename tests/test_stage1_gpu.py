@@ -69,7 +69,7 @@ def test_reorder_one_walker_bit_exact(gpu, workroot, case):
     assert H.same_files(o, g, H.STAGE1_FILES) == []
 
 
-def _check_invariants(d, L, res, dna, sdna):
+def _check_invariants(d, L, res, dna, sdna, heads_direct=True):
     clean = H.read_lines(os.path.join(d, "output", "input_clean.dna"), L)
     n = clean.shape[0]
     allid = np.concatenate([res["order"], res["order_s"]])
@@ -79,7 +79,8 @@ def _check_invariants(d, L, res, dna, sdna):
     assert set(np.unique(res["rev"]).tolist()) <= {ord("d"), ord("r")}
     head = res["flag"] == ord("0")
     assert np.all(res["pos"][head] == L) and np.all(res["pos"][~head] < L // 2)
-    assert np.all(res["rev"][head] == ord("d"))
+    if heads_direct:  # reference behaviour; with the left extension a chain may start with a reverse-complemented read
+        assert np.all(res["rev"][head] == ord("d"))
     if m:
         assert head[0]
     # temp.dna = reads gathered by order, reverse-complemented where flagged
@@ -93,19 +94,21 @@ def _check_invariants(d, L, res, dna, sdna):
     assert np.array_equal(sdna.reshape(-1, L + 1), clean[res["order_s"]])
 
 
-@pytest.mark.parametrize("walkers", [7, 64, 0])
-def test_reorder_many_walkers_invariants(gpu, workroot, walkers):
-    """Many concurrent walkers: every read exactly once, streams well formed, gathered reads consistent."""
+@pytest.mark.parametrize("extend", [-1, 1])
+@pytest.mark.parametrize("walkers", [1, 7, 64, 0])
+def test_reorder_many_walkers_invariants(gpu, workroot, walkers, extend):
+    """Many concurrent walkers, with and without the left extension of new chains: every read exactly once, streams
+    well formed, gathered reads consistent."""
     L = 100
     d = H.make_dataset(workroot, "m100", 60000, L, 400000, True, True, seed=5)
-    ctx = gpu.HarcGpu(L, walkers=walkers)
+    ctx = gpu.HarcGpu(L, walkers=walkers, extend=extend)
     ctx.load_reads(np.fromfile(os.path.join(d, "output", "input_clean.dna"), dtype=np.uint8))
     m, s, u = ctx.reorder()
     res = ctx.get_reorder()
     dna, sdna = ctx.get_reordered_reads()
     cnt = ctx.counters()
     ctx.close()
-    _check_invariants(d, L, res, dna, sdna)
+    _check_invariants(d, L, res, dna, sdna, heads_direct=extend < 0)
     assert cnt["steps"] >= m and cnt["restarts"] == u
     # chain heads + singletons = restarts
     assert int((res["flag"] == ord("0")).sum()) + s == u
