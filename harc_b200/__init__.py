@@ -18,7 +18,7 @@ EXPORTS = [
     "harcgpu_reorder_counts", "harcgpu_get_reorder", "harcgpu_get_reordered_reads", "harcgpu_get_counters",
     "harcgpu_set_stream", "harcgpu_load_pool", "harcgpu_encode", "harcgpu_get_encode_sizes", "harcgpu_get_set_sizes",
     "harcgpu_get_set", "harcgpu_get_globals", "harcgpu_reorder_dir", "harcgpu_encode_dir", "harcgpu_last_ms", "harcgpu_stream",
-    "harcgpu_load_pool_device", "harcgpu_launch_count",
+    "harcgpu_load_pool_device", "harcgpu_launch_count", "harcgpu_stage_nreads",
 ]
 
 
@@ -80,6 +80,7 @@ def load_library():
     lib.harcgpu_load_pool.argtypes = [vp, vp, vp, u32, vp, u32]
     lib.harcgpu_encode.argtypes = [vp]
     lib.harcgpu_load_pool_device.argtypes = [vp, vp, u32]
+    lib.harcgpu_stage_nreads.argtypes = [vp, vp, u32]
     lib.harcgpu_launch_count.restype = ctypes.c_uint64
     lib.harcgpu_get_encode_sizes.argtypes = [vp, ctypes.POINTER(EncodeSizes)]
     lib.harcgpu_get_set_sizes.argtypes = [vp, ctypes.c_int, ctypes.POINTER(SetSizes)]
@@ -217,6 +218,11 @@ class HarcGpu:
         nN = 0 if N_ascii is None else len(N_ascii) // (self.L + 1)
         self._keep3 = (singleton_ascii, order_s, N_ascii)
         self._ck(self.lib.harcgpu_load_pool(self.h, _ptr(singleton_ascii), _ptr(order_s), ns, _ptr(N_ascii), nN))
+
+    def stage_N_reads(self, N_ascii):
+        """Start the upload of input_N.dna now (overlaps stage I); load_pool(N_ascii=the same array) picks it up."""
+        self._keepN = N_ascii
+        self._ck(self.lib.harcgpu_stage_nreads(self.h, _ptr(N_ascii), len(N_ascii) // (self.L + 1)))
 
     def load_pool_device(self, dptr, n_N):
         self._ck(self.lib.harcgpu_load_pool_device(self.h, ctypes.c_void_p(dptr), n_N))

@@ -87,6 +87,7 @@ void harcgpu_destroy(harcgpu_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->st);
+	if (c->st_copy) { cudaStreamSynchronize(c->st_copy); cudaStreamDestroy(c->st_copy); cudaEventDestroy(c->ev_staged); cudaEventDestroy(c->ev_order); }
 	for (auto &b : c->live) cudaFree(b.p);
 	c->trim();
 	cudaEventDestroy(c->ev0);
@@ -250,6 +251,29 @@ int harcgpu_load_pool(harcgpu_ctx *c, const char *s_ascii, const uint32_t *order
 	if (!c || (n_N && !N_ascii)) { harcgpu_set_error("null argument"); return -1; }
 	CK(cudaSetDevice(c->device));
 	return s2_load_pool(c, s_ascii, order_s, n_s, N_ascii, n_N);
+}
+
+int harcgpu_stage_nreads(harcgpu_ctx *c, const char *N_ascii, uint32_t n_N)
+{
+	if (!c || (n_N && !N_ascii)) { harcgpu_set_error("null argument"); return -1; }
+	CK(cudaSetDevice(c->device));
+	if (!c->st_copy) {
+		CK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
+	}
+	c->release(c->staged_N);
+	c->staged_N = nullptr; c->staged_host = nullptr; c->staged_n = 0;
+	if (!n_N) return 0;
+	const size_t bytes = (size_t)n_N * (c->L + 1);
+	if (c->alloc(&c->staged_N, bytes + 16)) return -1;
+	// the block may still be in use by work queued on the compute stream: order the copy behind it
+	CK(cudaEventRecord(c->ev_order, c->st));
+	CK(cudaStreamWaitEvent(c->st_copy, c->ev_order, 0));
+	CK(cudaMemcpyAsync(c->staged_N, N_ascii, bytes, cudaMemcpyHostToDevice, c->st_copy));
+	CK(cudaEventRecord(c->ev_staged, c->st_copy));
+	c->staged_host = N_ascii; c->staged_n = n_N;
+	return 0;
 }
 
 int harcgpu_load_pool_device(harcgpu_ctx *c, const void *d_N_ascii, uint32_t n_N)

@@ -46,6 +46,12 @@ struct harcgpu_ctx {
 	u64 *sreads = nullptr;  // [m][NW] stream reads, already reverse-complemented where flagged
 	u32 *s_order = nullptr;
 	u8 *s_rev = nullptr, *s_flag = nullptr, *s_pos = nullptr;
+	// input_N.dna uploaded ahead of time on a copy stream (harcgpu_stage_nreads)
+	cudaStream_t st_copy = nullptr;
+	cudaEvent_t ev_staged = nullptr, ev_order = nullptr;
+	char *staged_N = nullptr;
+	const char *staged_host = nullptr;
+	u32 staged_n = 0;
 	bool pool_set = false;
 	u32 n_s = 0, n_N = 0;   // pool = n_s singletons ++ n_N reads with N
 	u64 *pool = nullptr;    // [n_s+n_N][NW] 2-bit codes with N stored as 0

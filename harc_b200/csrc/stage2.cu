@@ -582,7 +582,12 @@ static int load_pool_impl(harcgpu_ctx *c, const char *s_ascii, const u32 *order_
 	}
 	if (n_N) {
 		char *d = nullptr;
-		if (!d_N) {
+		if (!d_N && c->staged_N && c->staged_host == h_N && c->staged_n == n_N) {
+			// uploaded ahead of time by harcgpu_stage_nreads: only wait for that copy
+			CK(cudaStreamWaitEvent(st, c->ev_staged, 0));
+			d = c->staged_N;
+			c->staged_N = nullptr; c->staged_host = nullptr; c->staged_n = 0;
+		} else if (!d_N) {
 			if (c->alloc(&d, n_N * line + 16)) return -1;
 			CK(cudaMemcpyAsync(d, h_N, n_N * line, cudaMemcpyHostToDevice, st));
 		}

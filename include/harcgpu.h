@@ -110,6 +110,10 @@ int harcgpu_set_stream(harcgpu_ctx *ctx, const char *temp_dna, const char *flag,
  * after harcgpu_reorder() on the same context (the singletons are then taken from the device). */
 int harcgpu_load_pool(harcgpu_ctx *ctx, const char *singleton_ascii, const uint32_t *order_s, uint32_t n_s,
                       const char *N_ascii, uint32_t n_N);
+/* Optional: start the upload of input_N.dna on a copy stream and return at once, so that it overlaps stage I.  A later
+ * harcgpu_load_pool with the same N_ascii / n_N takes the uploaded copy.  N_ascii must stay valid (and should be
+ * page-locked for the copy to be asynchronous) until then. */
+int harcgpu_stage_nreads(harcgpu_ctx *ctx, const char *N_ascii, uint32_t n_N);
 /* Same with the N reads already resident in device memory (16-byte aligned) and the singletons taken from
  * harcgpu_reorder() on this context (bench: the kernel-only figure). */
 int harcgpu_load_pool_device(harcgpu_ctx *ctx, const void *d_N_ascii, uint32_t n_N);
