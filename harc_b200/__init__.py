@@ -19,6 +19,7 @@ EXPORTS = [
     "harcgpu_set_stream", "harcgpu_load_pool", "harcgpu_encode", "harcgpu_get_encode_sizes", "harcgpu_get_set_sizes",
     "harcgpu_get_set", "harcgpu_get_globals", "harcgpu_reorder_dir", "harcgpu_encode_dir", "harcgpu_last_ms", "harcgpu_stream",
     "harcgpu_load_pool_device", "harcgpu_launch_count", "harcgpu_stage_nreads",
+    "harcgpu_shard_init", "harcgpu_shard_connect", "harcgpu_shard_reset", "harcgpu_set_pool_exchange", "harcgpu_load_pool_ids",
 ]
 
 
@@ -48,6 +49,8 @@ class Counters(ctypes.Structure):
 
 
 _lib = None
+# hook of harcgpu_set_pool_exchange: int fn(void *user, void *d_best, uint64_t count)
+POOL_EXCHANGE = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64)
 
 
 def load_library():
@@ -81,6 +84,11 @@ def load_library():
     lib.harcgpu_encode.argtypes = [vp]
     lib.harcgpu_load_pool_device.argtypes = [vp, vp, u32]
     lib.harcgpu_stage_nreads.argtypes = [vp, vp, u32]
+    lib.harcgpu_shard_init.argtypes = [vp, ctypes.c_int, ctypes.c_int, u32, vp]
+    lib.harcgpu_shard_connect.argtypes = [vp, vp]
+    lib.harcgpu_shard_reset.argtypes = [vp]
+    lib.harcgpu_set_pool_exchange.argtypes = [vp, POOL_EXCHANGE, vp]
+    lib.harcgpu_load_pool_ids.argtypes = [vp, vp, u32, vp, u32]
     lib.harcgpu_launch_count.restype = ctypes.c_uint64
     lib.harcgpu_get_encode_sizes.argtypes = [vp, ctypes.POINTER(EncodeSizes)]
     lib.harcgpu_get_set_sizes.argtypes = [vp, ctypes.c_int, ctypes.POINTER(SetSizes)]
@@ -223,6 +231,41 @@ class HarcGpu:
         """Start the upload of input_N.dna now (overlaps stage I); load_pool(N_ascii=the same array) picks it up."""
         self._keepN = N_ascii
         self._ck(self.lib.harcgpu_stage_nreads(self.h, _ptr(N_ascii), len(N_ascii) // (self.L + 1)))
+
+    # ---- one job on several GPUs (see harc_b200/multi.py for the driver)
+    def shard_init(self, rank, world, n_total):
+        h = ctypes.create_string_buffer(64)
+        self._ck(self.lib.harcgpu_shard_init(self.h, rank, world, n_total, ctypes.cast(h, ctypes.c_void_p)))
+        return h.raw
+
+    def shard_connect(self, handles):
+        buf = ctypes.create_string_buffer(b"".join(handles), 64 * len(handles))
+        self._ck(self.lib.harcgpu_shard_connect(self.h, ctypes.cast(buf, ctypes.c_void_p)))
+
+    def shard_reset(self):
+        self._ck(self.lib.harcgpu_shard_reset(self.h))
+
+    def set_pool_exchange(self, fn):
+        """fn(device_pointer, count) -> None must min-reduce the int64 array over all ranks (None removes the hook)."""
+        if fn is None:
+            self._hook = POOL_EXCHANGE(0)
+        else:
+            def tramp(user, ptr, count):
+                try:
+                    fn(ptr, count)
+                    return 0
+                except Exception:  # never let an exception cross the C boundary
+                    import traceback
+                    traceback.print_exc()
+                    return -1
+            self._hook = POOL_EXCHANGE(tramp)
+        self._ck(self.lib.harcgpu_set_pool_exchange(self.h, self._hook, None))
+
+    def load_pool_ids(self, singleton_ids, N_ascii=None):
+        ids = np.ascontiguousarray(singleton_ids, dtype=np.uint32)
+        nN = 0 if N_ascii is None else len(N_ascii) // (self.L + 1)
+        self._keep3 = (ids, N_ascii)
+        self._ck(self.lib.harcgpu_load_pool_ids(self.h, _ptr(ids), len(ids), _ptr(N_ascii), nN))
 
     def load_pool_device(self, dptr, n_N):
         self._ck(self.lib.harcgpu_load_pool_device(self.h, ctypes.c_void_p(dptr), n_N))

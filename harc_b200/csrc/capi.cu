@@ -2,6 +2,7 @@
 #include "ctx.h"
 #include <stdarg.h>
 #include <string.h>
+#include <algorithm>
 #include <sys/stat.h>
 #include <string>
 #include <vector>
@@ -17,6 +18,7 @@ void harcgpu_set_error(const char *fmt, ...)
 }
 
 extern "C" {
+static void shard_close(harcgpu_ctx *c);
 
 const char *harcgpu_last_error(void) { return g_err; }
 uint64_t harcgpu_launch_count(void) { return g_harcgpu_launches; }
@@ -87,6 +89,7 @@ void harcgpu_destroy(harcgpu_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->st);
+	shard_close(c);
 	if (c->st_copy) { cudaStreamSynchronize(c->st_copy); cudaStreamDestroy(c->st_copy); cudaEventDestroy(c->ev_staged); cudaEventDestroy(c->ev_order); }
 	for (auto &b : c->live) cudaFree(b.p);
 	c->trim();
@@ -181,6 +184,69 @@ int harcgpu_reorder(harcgpu_ctx *c)
 	return s1_reorder(c);
 }
 
+// ---- one job on several GPUs -------------------------------------------------------------------------------
+static void shard_close(harcgpu_ctx *c)
+{
+	for (int r = 0; r < 8; r++) {
+		if (c->seg[r] && c->seg_opened[r]) cudaIpcCloseMemHandle(c->seg[r]);
+		else if (c->seg[r]) c->release(c->seg[r]);
+		c->seg[r] = nullptr; c->seg_opened[r] = false;
+	}
+	c->shard_world = 1; c->shard_rank = 0; c->shard_n = 0; c->seg_per = 0; c->shard_ready = false;
+}
+
+int harcgpu_shard_init(harcgpu_ctx *c, int rank, int world, uint32_t n_total, void *ipc_handle_out)
+{
+	if (!c || !ipc_handle_out || world < 1 || world > 8 || rank < 0 || rank >= world) { harcgpu_set_error("bad shard arguments (1..8 GPUs)"); return -1; }
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->st));
+	shard_close(c);
+	c->shard_rank = rank; c->shard_world = world; c->shard_n = n_total;
+	c->seg_per = (uint32_t)((((uint64_t)n_total + world - 1) / world + 31) / 32 * 32);
+	if (c->seg_per == 0) c->seg_per = 32;
+	if (c->alloc(&c->seg[rank], (size_t)c->seg_per / 32)) return -1;
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	cudaIpcMemHandle_t h;
+	CK(cudaIpcGetMemHandle(&h, c->seg[rank]));
+	memcpy(ipc_handle_out, &h, sizeof h);
+	return 0;
+}
+
+int harcgpu_shard_connect(harcgpu_ctx *c, const void *handles)
+{
+	if (!c || !handles || c->shard_world < 1 || !c->seg[c->shard_rank]) { harcgpu_set_error("harcgpu_shard_init first"); return -1; }
+	CK(cudaSetDevice(c->device));
+	for (int r = 0; r < c->shard_world; r++) {
+		if (r == c->shard_rank) continue;
+		cudaIpcMemHandle_t h;
+		memcpy(&h, (const char *)handles + 64 * (size_t)r, sizeof h);
+		void *p = nullptr;
+		CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		c->seg[r] = (u32 *)p;
+		c->seg_opened[r] = true;
+	}
+	return 0;
+}
+
+int harcgpu_shard_reset(harcgpu_ctx *c)
+{
+	if (!c || c->shard_world < 2 || !c->seg[c->shard_rank]) { harcgpu_set_error("not a sharded context"); return -1; }
+	CK(cudaSetDevice(c->device));
+	const u64 lo = std::min<u64>((u64)c->shard_rank * c->seg_per, c->shard_n), hi = std::min<u64>(lo + c->seg_per, c->shard_n);
+	CK(cudaMemsetAsync(c->seg[c->shard_rank], 0, (size_t)c->seg_per / 8, c->st));
+	if (s1_init_claim(c, c->seg[c->shard_rank], (u32)(hi - lo))) return -1;
+	CK(cudaStreamSynchronize(c->st));
+	c->shard_ready = true;
+	return 0;
+}
+
+int harcgpu_set_pool_exchange(harcgpu_ctx *c, int (*fn)(void *, void *, uint64_t), void *user)
+{
+	if (!c) { harcgpu_set_error("null argument"); return -1; }
+	c->pool_exchange = fn; c->pool_exchange_user = user;
+	return 0;
+}
+
 int harcgpu_reorder_counts(harcgpu_ctx *c, uint32_t *nm, uint32_t *ns, uint32_t *nu)
 {
 	if (!c || !c->reordered) { harcgpu_set_error("reorder first"); return -1; }
@@ -251,6 +317,13 @@ int harcgpu_load_pool(harcgpu_ctx *c, const char *s_ascii, const uint32_t *order
 	if (!c || (n_N && !N_ascii)) { harcgpu_set_error("null argument"); return -1; }
 	CK(cudaSetDevice(c->device));
 	return s2_load_pool(c, s_ascii, order_s, n_s, N_ascii, n_N);
+}
+
+int harcgpu_load_pool_ids(harcgpu_ctx *c, const uint32_t *singleton_ids, uint32_t n_s, const char *N_ascii, uint32_t n_N)
+{
+	if (!c || (n_N && !N_ascii) || (n_s && !singleton_ids)) { harcgpu_set_error("null argument"); return -1; }
+	CK(cudaSetDevice(c->device));
+	return s2_load_pool_ids(c, singleton_ids, n_s, N_ascii, n_N);
 }
 
 int harcgpu_stage_nreads(harcgpu_ctx *c, const char *N_ascii, uint32_t n_N)

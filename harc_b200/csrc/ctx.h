@@ -34,6 +34,14 @@ struct harcgpu_ctx {
 	long long *gpos = nullptr;
 	u64 *counters = nullptr; // 8 x u64
 	u32 walkers_used = 0;
+	// one job on several GPUs (harcgpu_shard_*): claim bitmap cut into contiguous id ranges, one per GPU
+	int shard_rank = 0, shard_world = 1;
+	u32 shard_n = 0, seg_per = 0;
+	u32 *seg[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // seg[shard_rank] is local
+	bool seg_opened[8] = { false, false, false, false, false, false, false, false };
+	bool shard_ready = false;
+	int (*pool_exchange)(void *user, void *d_best, uint64_t count) = nullptr;
+	void *pool_exchange_user = nullptr;
 	// finalized stage I streams (device)
 	bool reordered = false;
 	u32 n_matched = 0, n_single = 0, n_unmatched = 0;
@@ -144,6 +152,8 @@ struct harcgpu_ctx {
 	}
 };
 
+// walk.cu
+int s1_init_claim(harcgpu_ctx *c, u32 *claim, u32 n);
 // stage1.cu
 int s1_pack_reads(harcgpu_ctx *c, const void *d_ascii, u32 n);
 int s1_packN(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *out2, u64 *outN);
@@ -156,4 +166,5 @@ int s2_set_stream_from_stage1(harcgpu_ctx *c);
 int s2_set_stream_host(harcgpu_ctx *c, const char *dna, const char *flag, const u8 *pos, const u32 *order, const char *rev, u32 n);
 int s2_load_pool(harcgpu_ctx *c, const char *s_ascii, const u32 *order_s, u32 n_s, const char *N_ascii, u32 n_N);
 int s2_load_pool_dev(harcgpu_ctx *c, const void *d_N_ascii, u32 n_N);
+int s2_load_pool_ids(harcgpu_ctx *c, const u32 *ids, u32 n_s, const char *N_ascii, u32 n_N);
 int s2_encode(harcgpu_ctx *c);

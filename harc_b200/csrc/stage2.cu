@@ -20,7 +20,11 @@
 
 namespace {
 constexpr u32 CAP1 = 10000001u; // encoder.cpp:226: a contig is cut once list_size > 10000000
-constexpr u64 NOBEST = ~0ull;
+// priority word of a pool read: rank << 56 | column << 2 | probe kind.  Both sentinels are positive as int64 so that the
+// multi-GPU exchange can be a plain all-reduce(min) over int64.
+constexpr u64 NOBEST = 0x7fffffffffffffffull;    // no contig took the read
+constexpr u64 ELSEWHERE = 0x7ffffffffffffffeull; // another GPU's contig took it (or: unaligned, and rank 0 writes those)
+constexpr int RANK_SHIFT = 56;
 
 __device__ __forceinline__ u64 revpairs64(u64 x)
 {
@@ -181,6 +185,7 @@ struct PoolArgs {
 	DictView d[2];
 	int L, thresh_s, maxsearch;
 	u64 *best;
+	u64 rank_bits; // rank << RANK_SHIFT
 };
 
 __device__ __forceinline__ u64 spread2to3(u64 k2, int nb) // base t: 2-bit code c -> 3-bit code 2c at bits 3t
@@ -232,7 +237,7 @@ __global__ void __launch_bounds__(128) pool_probe_kernel(PoolArgs a)
 			int d = 0;
 #pragma unroll
 			for (int k = 0; k < NW; k++) d += __popcll((rev ? rc[k] : w[k]) ^ __ldg(&p2[k])) + __popcll(__ldg(&pn[k]));
-			if (d <= a.thresh_s) atomicMin(&a.best[rid], (g << 2) | (u64)q);
+			if (d <= a.thresh_s) atomicMin(&a.best[rid], a.rank_bits | (g << 2) | (u64)q);
 		}
 	}
 }
@@ -242,11 +247,21 @@ __global__ void __launch_bounds__(256) fill64_kernel(u64 *p, size_t n, u64 v)
 	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) p[i] = v;
 }
+// after the exchange: keep the reads this GPU's contigs won (rank bits stripped), mark the others
+__global__ void __launch_bounds__(256) best_localize_kernel(u64 *best, u32 P, int rank)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P) return;
+	u64 b = best[i];
+	if (b == NOBEST) { if (rank != 0) best[i] = ELSEWHERE; }
+	else if ((int)(b >> RANK_SHIFT) != rank) best[i] = ELSEWHERE;
+	else best[i] = b & ((1ull << RANK_SHIFT) - 1);
+}
 // aligned pool reads in DESCENDING id order (the bin scan order, encoder.cpp:293), then stably sorted by priority
 __global__ void __launch_bounds__(256) aligned_flag_kernel(const u64 *__restrict__ best, u32 P, u32 *__restrict__ af)
 {
 	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < P) af[i] = best[P - 1 - i] != NOBEST;
+	if (i < P) af[i] = best[P - 1 - i] < ELSEWHERE;
 }
 __global__ void __launch_bounds__(256) aligned_compact_kernel(const u64 *__restrict__ best, const u32 *__restrict__ af, const u32 *__restrict__ ex,
                                                               u32 P, u64 *__restrict__ prio, u32 *__restrict__ rid)
@@ -551,12 +566,15 @@ int s2_set_stream_host(harcgpu_ctx *c, const char *dna, const char *flag, const 
 }
 
 // encoder.cpp:823-872 + 132-148.  d_N: device buffer with the N reads (16-byte aligned) or null; h_N: host buffer or null.
-static int load_pool_impl(harcgpu_ctx *c, const char *s_ascii, const u32 *order_s, u32 n_s, const char *h_N, const void *d_N, u32 n_N)
+// by_id: the singletons are given as ids into the reads resident on this context (order_s on the host, s_ascii null)
+static int load_pool_impl(harcgpu_ctx *c, const char *s_ascii, const u32 *order_s, u32 n_s, const char *h_N, const void *d_N, u32 n_N,
+                          bool by_id = false)
 {
 	free_pool(c);
 	cudaStream_t st = c->st;
-	const bool from_stage1 = (s_ascii == nullptr && order_s == nullptr && n_s == 0 && c->reordered);
+	const bool from_stage1 = !by_id && (s_ascii == nullptr && order_s == nullptr && n_s == 0 && c->reordered);
 	if (from_stage1) n_s = c->n_single;
+	else if (by_id) { if (n_s && (!order_s || !c->reads)) { harcgpu_set_error("singleton ids need the reads of this context"); return -1; } }
 	else if (n_s && (!s_ascii || !order_s)) { harcgpu_set_error("singleton reads and their order are both needed"); return -1; }
 	const u64 P64 = (u64)n_s + n_N;
 	if (P64 > 0xfffffff0ull) { harcgpu_set_error("pool too large"); return -1; }
@@ -565,7 +583,12 @@ static int load_pool_impl(harcgpu_ctx *c, const char *s_ascii, const u32 *order_
 	if (c->alloc(&c->pool, (size_t)P * c->NW) || c->alloc(&c->poolN, (size_t)P * c->NW) || c->alloc(&c->pool_order, P)) return -1;
 	if (P) CK(cudaMemsetAsync(c->poolN, 0, (size_t)P * c->NW * 8, st));
 	const size_t line = (size_t)c->L + 1;
-	if (n_s) {
+	if (n_s && by_id) {
+		CK(cudaMemcpyAsync(c->pool_order, order_s, 4 * (size_t)n_s, cudaMemcpyHostToDevice, st));
+		DISPATCH_NW(c->NW, (gather_stream_kernel<NW><<<KL + cdiv(n_s, 128), 128, 0, st>>>(c->reads, c->pool_order, nullptr, n_s, c->L, c->pool)));
+		CK(cudaGetLastError());
+		CK(cudaStreamSynchronize(st));
+	} else if (n_s) {
 		if (from_stage1) {
 			DISPATCH_NW(c->NW, (gather_stream_kernel<NW><<<KL + cdiv(n_s, 128), 128, 0, st>>>(c->reads, c->order_s, nullptr, n_s, c->L, c->pool)));
 			CK(cudaGetLastError());
@@ -611,6 +634,10 @@ static int load_pool_impl(harcgpu_ctx *c, const char *s_ascii, const u32 *order_
 int s2_load_pool(harcgpu_ctx *c, const char *s_ascii, const u32 *order_s, u32 n_s, const char *N_ascii, u32 n_N)
 {
 	return load_pool_impl(c, s_ascii, order_s, n_s, N_ascii, nullptr, n_N);
+}
+int s2_load_pool_ids(harcgpu_ctx *c, const u32 *ids, u32 n_s, const char *N_ascii, u32 n_N)
+{
+	return load_pool_impl(c, nullptr, ids, n_s, N_ascii, nullptr, n_N, true);
 }
 int s2_load_pool_dev(harcgpu_ctx *c, const void *d_N_ascii, u32 n_N) { return load_pool_impl(c, nullptr, nullptr, 0, nullptr, d_N_ascii, n_N); }
 
@@ -668,7 +695,7 @@ int s2_encode(harcgpu_ctx *c)
 	// ---- pool re-alignment
 	u64 *best = nullptr, *prio_u = nullptr, *iprio = nullptr;
 	u32 *af = nullptr, *exa = nullptr, *rid_u = nullptr, *irid = nullptr;
-	u32 M = 0;
+	u32 M = 0, M_single = 0;
 	if (c->alloc(&best, P)) return -1;
 	if (P) {
 		fill64_kernel<<<KL + cdiv(P, 256), 256, 0, st>>>(best, P, NOBEST);
@@ -683,16 +710,31 @@ int s2_encode(harcgpu_ctx *c)
 			a.d[l].dstart = c->d2[l].bitpos / 3; a.d[l].dend = a.d[l].dstart + c->d2[l].nbits / 3 - 1;
 		}
 		a.L = L; a.thresh_s = c->p.thresh_s; a.maxsearch = c->p.maxsearch; a.best = best;
+		a.rank_bits = (u64)(c->shard_world > 1 ? c->shard_rank : 0) << RANK_SHIFT;
 		u64 nwin = TOT - L + 1;
 		DISPATCH_NW(NWv, (pool_probe_kernel<NW><<<KL + cdiv(nwin, 128), 128, 0, st>>>(a)));
 		CK(cudaGetLastError());
+	}
+	if (P && c->shard_world > 1) {
+		// one job on several GPUs: every GPU probed the same pool against its own contigs; the smallest priority over
+		// all GPUs wins (all-reduce(min) done by the caller's exchange hook, e.g. NCCL through torch.distributed)
+		if (!c->pool_exchange) { harcgpu_set_error("sharded encode needs harcgpu_set_pool_exchange"); return -1; }
+		CK(cudaStreamSynchronize(st));
+		if (c->pool_exchange(c->pool_exchange_user, best, P)) { harcgpu_set_error("pool exchange hook failed"); return -1; }
+		best_localize_kernel<<<KL + cdiv(P, 256), 256, 0, st>>>(best, P, c->shard_rank);
+		CK(cudaGetLastError());
+	}
+	if (P && ((m && TOT >= (u64)L) || c->shard_world > 1)) {
 		if (c->alloc(&af, P) || c->alloc(&exa, P) || c->alloc(&prio_u, P) || c->alloc(&rid_u, P)) return -1;
 		aligned_flag_kernel<<<KL + cdiv(P, 256), 256, 0, st>>>(best, P, af);
 		if (exclusive_scan_u32(af, exa, P, scan_tmp, d_tot32, st)) return -1;
 		aligned_compact_kernel<<<KL + cdiv(P, 256), 256, 0, st>>>(best, af, exa, P, prio_u, rid_u);
 		CK(cudaGetLastError());
 		CK(cudaMemcpyAsync(&M, d_tot32, 4, cudaMemcpyDeviceToHost, st));
+		u32 before = 0; // aligned reads among the ids >= n_s (the flags run from the highest id down)
+		if (n_s && n_s < P) CK(cudaMemcpyAsync(&before, exa + (P - n_s), 4, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
+		M_single = n_s ? M - (n_s < P ? before : 0u) : 0u;
 	}
 	if (c->alloc(&iprio, M) || c->alloc(&irid, M)) return -1;
 	if (M) {
@@ -840,6 +882,10 @@ int s2_encode(harcgpu_ctx *c)
 	c->esz.n_order = (u32)n_order; c->esz.n_order_N = (u32)n_order_N;
 	c->esz.singleton_bytes = sbytes; c->esz.singleton_tail = stail; c->esz.input_N_bytes = nbytesN;
 	c->esz.aligned_singletons = n_s - U_s; c->esz.aligned_N = c->n_N - U_N;
+	if (c->shard_world > 1) { // count what THIS GPU's contigs took
+		c->esz.aligned_singletons = M_single;
+		c->esz.aligned_N = M - M_single;
+	}
 	c->s2_keep.push_back(posb); c->s2_keep.push_back(noise); c->s2_keep.push_back(noisepos);
 	void *tmp[] = { ns, ex, nat_idx, cs, cid, cstart, inc, G, scan_tmp, d_tot32, d_tot64, cons2, best, prio_u, iprio, af, exa, rid_u, irid,
 	                f_src, f_kind, f_col, nm1, noff, revc, isN, exN, ordv, uf, exU, ulist, d_tail };

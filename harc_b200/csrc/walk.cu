@@ -40,7 +40,14 @@ struct WalkArgs {
 	int L, maxmatch, thresh, maxsearch, numdict, extend;
 	DictView d[2];
 	int kbits[2];
+	// claim bitmap (1 = unclaimed).  One GPU: `claim` covers all n reads.  One job on several GPUs: the bitmap is cut into
+	// `world` contiguous id ranges of `seg_per` reads, range r lives in the memory of GPU r (`seg[r]`, mapped through CUDA
+	// IPC, read and claimed over NVLink); this GPU's walkers start and restart only inside its own range
+	// [base, base + n_loc), whose words are `claim`.
 	u32 *claim;
+	u32 *seg[8];
+	u32 seg_per, base, n_loc;
+	int world;
 	u32 *stripe_done;
 	u32 walkers;
 	// forward record log: chunks of CHUNK records, ordered at finalize by (walker, sequence)
@@ -200,10 +207,16 @@ __device__ __forceinline__ int hamming(const WalkerSmem<NW> &s, const u64 (&rw)[
 	return d;
 }
 
-__device__ __forceinline__ bool try_claim(u32 *claim, u32 rid)
+__device__ __forceinline__ u32 *claim_word(const WalkArgs &a, u32 rid)
+{
+	if (a.world == 1) return a.claim + (rid >> 5);
+	const u32 r = rid / a.seg_per;
+	return a.seg[r] + ((rid - r * a.seg_per) >> 5);
+}
+__device__ __forceinline__ bool try_claim(const WalkArgs &a, u32 rid)
 {
 	u32 bit = 1u << (rid & 31);
-	u32 old = atomicAnd(&claim[rid >> 5], ~bit);
+	u32 old = atomicAnd(claim_word(a, rid), ~bit);
 	return (old & bit) != 0;
 }
 
@@ -257,14 +270,14 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 		s.chunk = NONE; s.fill = CHUNK; s.seq = 0;
 		s.lchunk = NONE; s.lfill = 0; s.lfirst = NONE; s.lcount = 0; s.j1 = 0; s.pend = 0; s.pend_f = 0;
 		s.stripe = wid; s.stripes_tried = 0;
-		s.cursor = wid < a.walkers ? (long long)((((u64)wid + 1) * a.n) / a.walkers) - 1 : -1;
+		s.cursor = wid < a.walkers ? (long long)((((u64)wid + 1) * a.n_loc) / a.walkers) - 1 : -1;
 	}
 	__syncwarp();
 	if (wid < a.walkers) {
 		// reorder.cpp:476-497: walker t starts at read t*(n/T).  (The reference thread gives up if that read is taken;
 		// here the walker looks for another head instead.)
-		const u32 start = (u32)((u64)wid * (a.n / a.walkers));
-		int ok = leader ? (int)try_claim(a.claim, start) : 0;
+		const u32 start = a.base + (u32)((u64)wid * (a.n_loc / a.walkers));
+		int ok = leader ? (int)try_claim(a, start) : 0;
 		ok = __shfl_sync(gmask, ok, gbase);
 		if (ok) { current = start; state = S_NEWHEAD; c_restart += leader; }
 		else state = S_RESTART;
@@ -290,7 +303,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 				u32 stripe = s.stripe, tried = s.stripes_tried;
 				long long cursor = s.cursor;
 				while (tried < a.walkers) {
-					const long long slo = (long long)(((u64)stripe * a.n) / a.walkers);
+					const long long slo = (long long)(((u64)stripe * a.n_loc) / a.walkers);
 					if (cursor < slo) {
 						// stripe exhausted: everything in it is claimed for good
 						if (leader) a.stripe_done[stripe] = 1u;
@@ -315,7 +328,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 							tried += span;
 						}
 						if (!found_stripe) { tried = a.walkers; break; }
-						cursor = (long long)((((u64)stripe + 1) * a.n) / a.walkers) - 1;
+						cursor = (long long)((((u64)stripe + 1) * a.n_loc) / a.walkers) - 1;
 						continue;
 					}
 					const long long topw = cursor >> 5;
@@ -329,10 +342,10 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 					const u32 wv = __shfl_sync(gmask, word, gbase + src);
 					const int bit = 31 - __clz(wv);
 					const u32 j = (u32)((topw - src) * 32 + bit);
-					int got = leader ? (int)try_claim(a.claim, j) : 0;
+					int got = leader ? (int)try_claim(a, a.base + j) : 0;
 					got = __shfl_sync(gmask, got, gbase);
 					cursor = (long long)j - 1; // j is claimed now, by this walker or by another one
-					if (got) { current = j; got_head = true; break; }
+					if (got) { current = a.base + j; got_head = true; break; }
 				}
 				if (leader) { s.stripe = stripe; s.stripes_tried = tried; s.cursor = cursor; }
 				if (got_head) { state = S_NEWHEAD; c_restart += leader; }
@@ -409,7 +422,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 					while (left > 0 && seen < a.maxsearch) {
 						left--;
 						const u32 rid = bin_entry(dv, lo, size, left);
-						const u32 cw = ldvol(&a.claim[rid >> 5]); // claim bit and read are fetched together
+						const u32 cw = ldvol(claim_word(a, rid)); // claim bit and read are fetched together
 						load_read<NW>(a.reads, rid, rw);
 						if (!((cw >> (rid & 31)) & 1u)) continue; // removed from the bin in the reference (505-514)
 						seen++;
@@ -426,7 +439,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 						const int win = __ffs(bal) - 1;
 						int got = 0;
 						if (sub == win) {
-							got = try_claim(a.claim, cand);
+							got = try_claim(a, cand);
 							if (!got) c_fail++;
 						}
 						got = __shfl_sync(gmask, got, gbase + win);
@@ -642,11 +655,20 @@ int resident_walkers(harcgpu_ctx *c, u32 *out)
 	default: harcgpu_set_error("unsupported read length %d / lanes per walker %d", c->L, (int)(Gv)); return -1; \
 	}
 
+int s1_init_claim(harcgpu_ctx *c, u32 *claim, u32 n)
+{
+	if (!n) return 0;
+	init_claim_kernel<<<KL + cdiv((n + 31) / 32, 256), 256, 0, c->st>>>(claim, n);
+	CK(cudaGetLastError());
+	return 0;
+}
+
 int s1_reorder(harcgpu_ctx *c)
 {
 	cudaStream_t st = c->st;
 	const u32 n = c->n;
 	c->reordered = false;
+	c->stream_set = false; c->pool_set = false; c->encoded = false; // stage II inputs derived from an earlier pass are stale now
 	c->release(c->order); c->release(c->order_s); c->release(c->rev); c->release(c->flag); c->release(c->pos);
 	c->order = c->order_s = nullptr; c->rev = c->flag = c->pos = nullptr;
 	c->n_matched = c->n_single = c->n_unmatched = 0;
@@ -665,9 +687,19 @@ int s1_reorder(harcgpu_ctx *c)
 	if (lanes != 8 && lanes != 16 && lanes != 32) { harcgpu_set_error("lanes_per_walker must be 8, 16 or 32"); return -1; }
 	DISPATCH_NW_G(c->NW, lanes, (rc = resident_walkers<NW, G>(c, &resident)));
 	if (rc) return rc;
+	// one job on several GPUs: this GPU's walkers own the id range [base, base + n_loc) for starts and restarts
+	const bool sharded = c->shard_world > 1;
+	if (sharded && (c->shard_n != n || !c->shard_ready)) {
+		harcgpu_set_error("sharded reorder: call harcgpu_shard_init/connect for these %u reads and harcgpu_shard_reset before every pass", n);
+		return -1;
+	}
+	c->shard_ready = false; // a sharded pass consumes the reset
+	const u32 base = sharded ? std::min<u64>((u64)c->shard_rank * c->seg_per, n) : 0u;
+	const u32 n_loc = sharded ? (u32)(std::min<u64>(((u64)c->shard_rank + 1) * c->seg_per, n) - base) : n;
 	const u32 per = c->p.reads_per_walker > 0 ? (u32)c->p.reads_per_walker : 4096u;
-	u32 walkers = c->p.walkers > 0 ? (u32)c->p.walkers : (u32)std::min<u64>(resident, std::max<u64>(1, n / per));
-	if (walkers > n) walkers = n;
+	u32 walkers = c->p.walkers > 0 ? (u32)c->p.walkers : (u32)std::min<u64>(resident, std::max<u64>(1, n_loc / per));
+	if (walkers > n_loc) walkers = n_loc;
+	if (walkers == 0) { c->reordered = true; c->ms["walk"] = 0; c->ms["finalize"] = 0; return 0; } // no read in this GPU's range
 	c->walkers_used = walkers;
 	// left extension: off for a single walker unless asked for (one walker without it = the reference at num_thr=1)
 	const int extend = c->p.extend > 0 ? 1 : (c->p.extend < 0 ? 0 : (walkers > 1 ? 1 : 0));
@@ -682,8 +714,10 @@ int s1_reorder(harcgpu_ctx *c)
 	if (extend && (c->alloc(&lrecs, (size_t)max_chunks * CHUNK) || c->alloc(&lprev, max_chunks))) return -1;
 	CK(cudaMemsetAsync(ctrs, 0, 8, st));
 	CK(cudaMemsetAsync(chunk_fill, 0, 4 * (size_t)max_chunks, st));
-	init_claim_kernel<<<KL + cdiv((n + 31) / 32, 256), 256, 0, st>>>(c->claim, n);
-	CK(cudaGetLastError());
+	if (!sharded) { // the sharded bitmap is initialised by harcgpu_shard_reset, before the barrier that precedes the walk
+		init_claim_kernel<<<KL + cdiv((n + 31) / 32, 256), 256, 0, st>>>(c->claim, n);
+		CK(cudaGetLastError());
+	}
 	u32 *stripe_done = nullptr;
 	if (c->alloc(&stripe_done, walkers)) return -1;
 	CK(cudaMemsetAsync(stripe_done, 0, 4 * (size_t)walkers, st));
@@ -697,7 +731,9 @@ int s1_reorder(harcgpu_ctx *c)
 		a.d[l].dstart = c->p.dict_start[ll]; a.d[l].dend = c->p.dict_end[ll];
 		a.kbits[l] = c->d1[ll].nbits;
 	}
-	a.claim = c->claim; a.stripe_done = stripe_done; a.walkers = walkers;
+	a.claim = sharded ? c->seg[c->shard_rank] : c->claim; a.stripe_done = stripe_done; a.walkers = walkers;
+	for (int r = 0; r < 8; r++) a.seg[r] = sharded && r < c->shard_world ? c->seg[r] : nullptr;
+	a.seg_per = sharded ? c->seg_per : 0u; a.base = base; a.n_loc = n_loc; a.world = sharded ? c->shard_world : 1;
 	a.recs = recs; a.chunk_key = chunk_key; a.chunk_fill = chunk_fill; a.chunk_ctr = ctrs; a.max_chunks = max_chunks;
 	a.lrecs = lrecs; a.lprev = lprev; a.lchunk_ctr = ctrs + 1; a.max_lchunks = max_chunks;
 	a.counters = c->counters;
@@ -741,7 +777,7 @@ int s1_reorder(harcgpu_ctx *c)
 	void *tmp[] = { recs, chunk_key, key_sorted, chunk_fill, ctrs, chunk_id, chunk_sorted, cm, cs, om, os, totals, scan_tmp, cub_tmp,
 	                stripe_done, lrecs, lprev };
 	for (void *q : tmp) c->release(q);
-	if ((u64)tot[0] + tot[1] != n) { harcgpu_set_error("reorder lost reads: %u matched + %u singletons != %u", tot[0], tot[1], n); return -1; }
+	if (!sharded && (u64)tot[0] + tot[1] != n) { harcgpu_set_error("reorder lost reads: %u matched + %u singletons != %u", tot[0], tot[1], n); return -1; }
 	c->reordered = true;
 	return 0;
 }

@@ -127,6 +127,27 @@ int harcgpu_get_set(harcgpu_ctx *ctx, int k, uint8_t *seq, char *seq_tail, uint8
 int harcgpu_get_globals(harcgpu_ctx *ctx, uint32_t *order, uint32_t *order_N, uint8_t *singleton,
                         char *singleton_tail, char *input_N);
 
+/* ---- one job on several GPUs of one box (one process and one context per GPU) -------------------------------
+ * Not in the reference (it is one process).  Every GPU holds all packed reads and both dictionaries; what is shared is
+ * the claimed-read bitmap (reorder.cpp:449 remainingreads + the lock arrays of reorder.cpp:436-442): it is cut into
+ * `world` contiguous id ranges, range r lives on GPU r and the other GPUs read and claim it through NVLink peer memory
+ * (CUDA IPC).  GPU r's walkers start and restart only inside range r but may claim any read, so the chains of all GPUs
+ * partition the read set exactly as the threads of the reference do.  Stage II then runs per GPU on its own chains
+ * (file set k = rank, encoder.cpp:169-196) against the same pool; which contig gets a pool read is settled by an
+ * all-reduce(min) over the priority array, done by the caller's hook (NCCL through torch.distributed in this repo).
+ * Call order per pass: load_reads (all reads, on every rank) -> shard_init -> [exchange the 64-byte handles] ->
+ * shard_connect -> build_dicts -> shard_reset -> [barrier] -> reorder -> [barrier] -> get_reorder (own singletons) ->
+ * [all-gather the singleton ids] -> load_pool_ids -> encode (calls the hook once) -> get_set(0) / get_globals. */
+int harcgpu_shard_init(harcgpu_ctx *ctx, int rank, int world, uint32_t n_total, void *ipc_handle_out /* 64 bytes */);
+int harcgpu_shard_connect(harcgpu_ctx *ctx, const void *handles /* world x 64 bytes, in rank order */);
+int harcgpu_shard_reset(harcgpu_ctx *ctx); /* re-arm this rank's range of the bitmap; barrier before the next reorder */
+/* Hook called once per harcgpu_encode of a sharded context with the device array of `count` int64 priorities: it must
+ * return 0 after replacing the array by its element-wise minimum over all ranks. */
+int harcgpu_set_pool_exchange(harcgpu_ctx *ctx, int (*fn)(void *user, void *d_best, uint64_t count), void *user);
+/* harcgpu_load_pool with the singletons given as ids into the reads of this context (the concatenation of all ranks'
+ * read_order.bin.singleton); unaligned pool reads are written by rank 0 only. */
+int harcgpu_load_pool_ids(harcgpu_ctx *ctx, const uint32_t *singleton_ids, uint32_t n_s, const char *N_ascii, uint32_t n_N);
+
 /* ---- the process contract, in-process --------------------------------------------------------------------- */
 /* `reorder.out <basedir>` (reorder.cpp:100-131) and `encoder.out <basedir>` (encoder.cpp:108-152): read and write
  * the files of SURVEY Appendix A under <basedir>/output/. */
