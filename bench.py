@@ -148,6 +148,10 @@ def main():
     ap.add_argument("--reads-per-walker", type=int, default=0)
     ap.add_argument("--extend", type=int, default=0)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--mode", default="read-sets", choices=["read-sets", "single-job"],
+                    help="N>1: read-sets = every rank compresses its own read set (weak scaling, no data-path collective); "
+                         "single-job = ONE read set of --reads on all ranks (strong scaling: shared claim bitmap over NVLink peer "
+                         "memory, all-gather of singleton ids, all-reduce(min) of pool claims)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer pass")
     args = ap.parse_args()
@@ -172,10 +176,13 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     # ---- workload: every rank owns an independent read set (seed differs per rank)
-    w = W.make(args.reads, L, args.genome, rc=False, errors=True, seed=args.seed + 7919 * rank)
+    single_job = args.mode == "single-job" and world > 1
+    w = W.make(args.reads, L, args.genome, rc=False, errors=True, seed=args.seed + (0 if single_job else 7919 * rank))
     n_clean, n_N = w["n_clean"], w["n_N"]
     h_clean = torch.from_numpy(w["clean"]).pin_memory()
     h_N = torch.from_numpy(w["withN"]).pin_memory()
@@ -191,9 +198,18 @@ def main():
     stream = torch.cuda.ExternalStream(ctx.stream())
     phases = ["pack", "dict", "walk", "finalize", "pooldict", "encode"]
 
+    if single_job:
+        from harc_b200 import multi
+        ctx.load_reads_device(d_clean.data_ptr(), n_clean)
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.shard_init(rank, world, n_clean))
+        ctx.shard_connect(handles)
+
     def step_device():
         ctx.load_reads_device(d_clean.data_ptr(), n_clean)
         ctx.build_dicts()
+        if single_job:
+            return multi.run_pass(ctx, dist, d_N.data_ptr(), rank, world, torch, n_N)["sizes"]
         ctx.reorder()
         ctx.load_pool_device(d_N.data_ptr(), n_N)
         return ctx.encode()
@@ -223,13 +239,18 @@ def main():
             host_ms[name] = host_ms.get(name, 0.0) + 1000.0 * (t[-1] - t[-2])
         ctx.load_reads(h_clean.numpy(), n_clean)
         lap("load_reads(H2D+pack)")
-        ctx.stage_N_reads(hN_np)  # upload of the reads with N overlaps stage I
-        ctx.reorder()
-        lap("reorder")
-        ctx.load_pool(None, None, hN_np)
-        lap("load_pool(H2D+dict)")
-        ctx.encode()
-        lap("encode")
+        if single_job:
+            ctx.build_dicts()
+            multi.run_pass(ctx, dist, hN_np, rank, world, torch)
+            lap("reorder+exchange+encode")
+        else:
+            ctx.stage_nreads(hN_np)  # upload of the reads with N overlaps stage I
+            ctx.reorder()
+            lap("reorder")
+            ctx.load_pool(None, None, hN_np)
+            lap("load_pool(H2D+dict)")
+            ctx.encode()
+            lap("encode")
         nbytes = 0
         cur[0] = 0
         for k in range(args.file_sets):
@@ -282,7 +303,7 @@ def main():
         host_ms.clear()
         ms_e2e, _, _ = timed(step_host, args.steps)
 
-    total_reads = (n_clean + n_N) * world
+    total_reads = (n_clean + n_N) * (1 if single_job else world)
     value = total_reads / (ms_dev / 1000.0) / 1e6
     e2e = total_reads / (ms_e2e / 1000.0) / 1e6
     if rank != 0:
@@ -307,11 +328,12 @@ def main():
         pass
     out = {
         "metric": METRIC, "value": value, "unit": "Mreads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "configs[1]: %d x %dbp reads, 1%% substitutions incl. N (gen_fastq_noRC -e model), %d bp synthetic genome, per GPU"
-                               % (args.reads, L, args.genome),
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong" if single_job else "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "configs[1]: %d x %dbp reads, 1%% substitutions incl. N (gen_fastq_noRC -e model), %d bp synthetic genome, %s"
+                               % (args.reads, L, args.genome, "ONE read set on all GPUs" if single_job else "per GPU"),
                    "reads_per_gpu": args.reads, "clean_reads": n_clean, "reads_with_N": n_N, "walkers": ctx.p.walkers or "auto",
-                   "file_sets": args.file_sets, "parallelism": "1 independent read set per GPU" if world > 1 else "single GPU",
+                   "file_sets": args.file_sets, "parallelism": ("single GPU" if world == 1 else "one job: claim bitmap in NVLink peer memory + all-gather/all-reduce(min) of pool claims"
+                                   if single_job else "1 independent read set per GPU"),
                    "l2": "inputs (%.1f GB ASCII, %.1f GB packed) exceed the 126 MB L2; no explicit flush" % ((n_clean + n_N) * 101 / 1e9, n_clean * 32 / 1e9)},
         "phases_ms": ph,
         "stage1": {"matched": m, "singletons": s, "chain_heads": u, "probes_per_read": cnt["probes"] / max(1, cnt["steps"]),

@@ -193,6 +193,13 @@ class HarcGpu:
         self._ck(self.lib.harcgpu_reorder_counts(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return a.value, b.value, c.value
 
+    def get_singleton_ids(self):
+        """read_order.bin.singleton only (the ids of this context's singletons)."""
+        _, s, _ = self.reorder_counts()
+        order_s = np.empty(s, dtype=np.uint32)
+        self._ck(self.lib.harcgpu_get_reorder(self.h, None, None, None, None, _ptr(order_s)))
+        return order_s
+
     def get_reorder(self):
         m, s, _ = self.reorder_counts()
         order = np.empty(m, dtype=np.uint32)
@@ -227,7 +234,7 @@ class HarcGpu:
         self._keep3 = (singleton_ascii, order_s, N_ascii)
         self._ck(self.lib.harcgpu_load_pool(self.h, _ptr(singleton_ascii), _ptr(order_s), ns, _ptr(N_ascii), nN))
 
-    def stage_N_reads(self, N_ascii):
+    def stage_nreads(self, N_ascii):
         """Start the upload of input_N.dna now (overlaps stage I); load_pool(N_ascii=the same array) picks it up."""
         self._keepN = N_ascii
         self._ck(self.lib.harcgpu_stage_nreads(self.h, _ptr(N_ascii), len(N_ascii) // (self.L + 1)))
@@ -261,11 +268,13 @@ class HarcGpu:
             self._hook = POOL_EXCHANGE(tramp)
         self._ck(self.lib.harcgpu_set_pool_exchange(self.h, self._hook, None))
 
-    def load_pool_ids(self, singleton_ids, N_ascii=None):
+    def load_pool_ids(self, singleton_ids, N_ascii=None, n_N=None):
+        """N_ascii: uint8 array, or a raw pointer (int; host or device memory) together with n_N."""
         ids = np.ascontiguousarray(singleton_ids, dtype=np.uint32)
-        nN = 0 if N_ascii is None else len(N_ascii) // (self.L + 1)
+        if n_N is None:
+            n_N = 0 if N_ascii is None else len(N_ascii) // (self.L + 1)
         self._keep3 = (ids, N_ascii)
-        self._ck(self.lib.harcgpu_load_pool_ids(self.h, _ptr(ids), len(ids), _ptr(N_ascii), nN))
+        self._ck(self.lib.harcgpu_load_pool_ids(self.h, _ptr(ids), len(ids), _ptr(N_ascii), n_N))
 
     def load_pool_device(self, dptr, n_N):
         self._ck(self.lib.harcgpu_load_pool_device(self.h, ctypes.c_void_p(dptr), n_N))

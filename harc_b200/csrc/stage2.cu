@@ -584,7 +584,7 @@ static int load_pool_impl(harcgpu_ctx *c, const char *s_ascii, const u32 *order_
 	if (P) CK(cudaMemsetAsync(c->poolN, 0, (size_t)P * c->NW * 8, st));
 	const size_t line = (size_t)c->L + 1;
 	if (n_s && by_id) {
-		CK(cudaMemcpyAsync(c->pool_order, order_s, 4 * (size_t)n_s, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(c->pool_order, order_s, 4 * (size_t)n_s, cudaMemcpyDefault, st)); // host or device ids
 		DISPATCH_NW(c->NW, (gather_stream_kernel<NW><<<KL + cdiv(n_s, 128), 128, 0, st>>>(c->reads, c->pool_order, nullptr, n_s, c->L, c->pool)));
 		CK(cudaGetLastError());
 		CK(cudaStreamSynchronize(st));
@@ -612,7 +612,7 @@ static int load_pool_impl(harcgpu_ctx *c, const char *s_ascii, const u32 *order_
 			c->staged_N = nullptr; c->staged_host = nullptr; c->staged_n = 0;
 		} else if (!d_N) {
 			if (c->alloc(&d, n_N * line + 16)) return -1;
-			CK(cudaMemcpyAsync(d, h_N, n_N * line, cudaMemcpyHostToDevice, st));
+			CK(cudaMemcpyAsync(d, h_N, n_N * line, cudaMemcpyDefault, st)); // host (or, for the bench, device) buffer
 		}
 		if (s1_packN(c, d_N ? d_N : d, n_N, c->pool + (size_t)n_s * c->NW, c->poolN + (size_t)n_s * c->NW)) return -1;
 		iota_off_kernel<<<KL + cdiv(n_N, 256), 256, 0, st>>>(c->pool_order + n_s, n_N); // order_s[i] = i - numreads_s (869-870)

@@ -45,6 +45,7 @@ struct WalkArgs {
 	// IPC, read and claimed over NVLink); this GPU's walkers start and restart only inside its own range
 	// [base, base + n_loc), whose words are `claim`.
 	u32 *claim;
+	u32 *hint; // sharded only: full-size local bitmap, bit cleared once this GPU knows the read is claimed (never authoritative)
 	u32 *seg[8];
 	u32 seg_per, base, n_loc;
 	int world;
@@ -213,10 +214,18 @@ __device__ __forceinline__ u32 *claim_word(const WalkArgs &a, u32 rid)
 	const u32 r = rid / a.seg_per;
 	return a.seg[r] + ((rid - r * a.seg_per) >> 5);
 }
+// word to TEST before fetching a candidate: the authoritative word for the own range, the local hint for a peer's range
+// (a stale hint only costs a failed remote claim, after which the hint is corrected)
+__device__ __forceinline__ const u32 *peek_word(const WalkArgs &a, u32 rid)
+{
+	if (a.world == 1) return a.claim + (rid >> 5);
+	return (rid - a.base < a.n_loc) ? a.claim + ((rid - a.base) >> 5) : a.hint + (rid >> 5);
+}
 __device__ __forceinline__ bool try_claim(const WalkArgs &a, u32 rid)
 {
 	u32 bit = 1u << (rid & 31);
 	u32 old = atomicAnd(claim_word(a, rid), ~bit);
+	if (a.world > 1 && rid - a.base >= a.n_loc) atomicAnd(a.hint + (rid >> 5), ~bit); // claimed now, by this GPU or by a peer
 	return (old & bit) != 0;
 }
 
@@ -422,7 +431,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 					while (left > 0 && seen < a.maxsearch) {
 						left--;
 						const u32 rid = bin_entry(dv, lo, size, left);
-						const u32 cw = ldvol(claim_word(a, rid)); // claim bit and read are fetched together
+						const u32 cw = ldvol(peek_word(a, rid)); // claim bit and read are fetched together
 						load_read<NW>(a.reads, rid, rw);
 						if (!((cw >> (rid & 31)) & 1u)) continue; // removed from the bin in the reference (505-514)
 						seen++;
@@ -714,10 +723,10 @@ int s1_reorder(harcgpu_ctx *c)
 	if (extend && (c->alloc(&lrecs, (size_t)max_chunks * CHUNK) || c->alloc(&lprev, max_chunks))) return -1;
 	CK(cudaMemsetAsync(ctrs, 0, 8, st));
 	CK(cudaMemsetAsync(chunk_fill, 0, 4 * (size_t)max_chunks, st));
-	if (!sharded) { // the sharded bitmap is initialised by harcgpu_shard_reset, before the barrier that precedes the walk
-		init_claim_kernel<<<KL + cdiv((n + 31) / 32, 256), 256, 0, st>>>(c->claim, n);
-		CK(cudaGetLastError());
-	}
+	// one GPU: the bitmap.  Sharded: the authoritative ranges are armed by harcgpu_shard_reset before the barrier that
+	// precedes the walk; c->claim serves as this GPU's hint bitmap for the peers' ranges.
+	init_claim_kernel<<<KL + cdiv((n + 31) / 32, 256), 256, 0, st>>>(c->claim, n);
+	CK(cudaGetLastError());
 	u32 *stripe_done = nullptr;
 	if (c->alloc(&stripe_done, walkers)) return -1;
 	CK(cudaMemsetAsync(stripe_done, 0, 4 * (size_t)walkers, st));
@@ -731,7 +740,7 @@ int s1_reorder(harcgpu_ctx *c)
 		a.d[l].dstart = c->p.dict_start[ll]; a.d[l].dend = c->p.dict_end[ll];
 		a.kbits[l] = c->d1[ll].nbits;
 	}
-	a.claim = sharded ? c->seg[c->shard_rank] : c->claim; a.stripe_done = stripe_done; a.walkers = walkers;
+	a.claim = sharded ? c->seg[c->shard_rank] : c->claim; a.hint = c->claim; a.stripe_done = stripe_done; a.walkers = walkers;
 	for (int r = 0; r < 8; r++) a.seg[r] = sharded && r < c->shard_world ? c->seg[r] : nullptr;
 	a.seg_per = sharded ? c->seg_per : 0u; a.base = base; a.n_loc = n_loc; a.world = sharded ? c->shard_world : 1;
 	a.recs = recs; a.chunk_key = chunk_key; a.chunk_fill = chunk_fill; a.chunk_ctr = ctrs; a.max_chunks = max_chunks;

@@ -33,19 +33,33 @@ def compress_sharded(ctx, dist, clean_ascii, N_ascii, rank=None, world=None):
     dist.all_gather_object(handles, handle)
     ctx.shard_connect(handles)
     ctx.build_dicts()
-    return run_pass(ctx, dist, N_ascii, rank, world, torch)
+    return fetch(ctx, run_pass(ctx, dist, N_ascii, rank, world, torch))
 
 
-def run_pass(ctx, dist, N_ascii, rank, world, torch):
+def gather_ids(mine, dist, world, torch):
+    """Concatenation, in rank order, of every rank's uint32 id list (NCCL all-gather of padded device tensors)."""
+    cnt = torch.tensor([len(mine)], dtype=torch.int64, device="cuda")
+    cnts = torch.empty(world, dtype=torch.int64, device="cuda")
+    dist.all_gather_into_tensor(cnts, cnt)
+    cnts = cnts.cpu().numpy()
+    cap = int(cnts.max()) if world else 0
+    if cap == 0:
+        return np.empty(0, dtype=np.uint32)
+    buf = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    buf[: len(mine)] = torch.from_numpy(mine.view(np.int32)).cuda()
+    allb = torch.empty(world * cap, dtype=torch.int32, device="cuda")
+    dist.all_gather_into_tensor(allb, buf)
+    h = allb.cpu().numpy().view(np.uint32).reshape(world, cap)
+    return np.concatenate([h[r, : int(cnts[r])] for r in range(world)])
+
+
+def run_pass(ctx, dist, N_ascii, rank, world, torch, n_N=None):
     """One timed pass on a connected context (reads loaded, dictionaries built)."""
     ctx.shard_reset()
     dist.barrier()                      # every range of the bitmap is armed before any walker claims
     m, s, u = ctx.reorder()
     dist.barrier()                      # nobody re-arms or frees its range while a peer still walks
-    mine = ctx.get_reorder()["order_s"]
-    parts = [None] * world
-    dist.all_gather_object(parts, mine)
-    pool_ids = np.concatenate(parts) if parts else mine
+    pool_ids = gather_ids(ctx.get_singleton_ids(), dist, world, torch)
 
     def exchange(ptr, count):
         t = _dev_tensor(ptr, count, torch)
@@ -53,9 +67,16 @@ def run_pass(ctx, dist, N_ascii, rank, world, torch):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         torch.cuda.synchronize()
     ctx.set_pool_exchange(exchange)
-    ctx.load_pool_ids(pool_ids, N_ascii)
+    ctx.load_pool_ids(pool_ids, N_ascii, n_N)
     es = ctx.encode()
-    return dict(set=ctx.get_set(0), glob=ctx.get_globals(), sizes=es, counts=(m, s, u), pool=len(pool_ids))
+    return dict(sizes=es, counts=(m, s, u), pool=len(pool_ids))
+
+
+def fetch(ctx, res, empty=np.empty):
+    """Copy this rank's file set and its share of the global streams to the host."""
+    res["set"] = ctx.get_set(0, empty)
+    res["glob"] = ctx.get_globals(empty)
+    return res
 
 
 def assemble_globals(parts, L):

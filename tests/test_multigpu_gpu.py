@@ -37,7 +37,7 @@ def _worker(rank, world, port, src, dst, L):
     ctx = harc_b200.HarcGpu(L, device=rank, file_sets=1)
     res = multi.compress_sharded(ctx, dist, clean, withN)
     # a second pass on the connected context must work too (bench loop)
-    res = multi.run_pass(ctx, dist, withN, rank, world, torch)
+    res = multi.fetch(ctx, multi.run_pass(ctx, dist, withN, rank, world, torch))
     multi.write_outputs(dst, rank, world, res, L, dist)
     m, s, u = res["counts"]
     stats = [None] * world
