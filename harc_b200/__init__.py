@@ -20,6 +20,7 @@ EXPORTS = [
     "harcgpu_get_set", "harcgpu_get_globals", "harcgpu_reorder_dir", "harcgpu_encode_dir", "harcgpu_last_ms", "harcgpu_stream",
     "harcgpu_load_pool_device", "harcgpu_launch_count", "harcgpu_stage_nreads",
     "harcgpu_shard_init", "harcgpu_shard_connect", "harcgpu_shard_reset", "harcgpu_set_pool_exchange", "harcgpu_load_pool_ids",
+    "harcgpu_get_packed_order",
 ]
 
 
@@ -89,6 +90,7 @@ def load_library():
     lib.harcgpu_shard_reset.argtypes = [vp]
     lib.harcgpu_set_pool_exchange.argtypes = [vp, POOL_EXCHANGE, vp]
     lib.harcgpu_load_pool_ids.argtypes = [vp, vp, u32, vp, u32]
+    lib.harcgpu_get_packed_order.argtypes = [vp, vp, vp, vp, vp]
     lib.harcgpu_launch_count.restype = ctypes.c_uint64
     lib.harcgpu_get_encode_sizes.argtypes = [vp, ctypes.POINTER(EncodeSizes)]
     lib.harcgpu_get_set_sizes.argtypes = [vp, ctypes.c_int, ctypes.POINTER(SetSizes)]
@@ -311,6 +313,15 @@ class HarcGpu:
                                               _ptr(o["singleton_tail"]), _ptr(o["input_N"])))
         o["singleton_tail"] = o["singleton_tail"][: s.singleton_tail]
         return o
+
+    def get_packed_order(self):
+        """(read_order.bin as pack_order.cpp would rewrite it, read_order.bin.tail) for the -p mode."""
+        nb, nt = ctypes.c_uint64(), ctypes.c_uint32()
+        self._ck(self.lib.harcgpu_get_packed_order(self.h, None, None, ctypes.byref(nb), ctypes.byref(nt)))
+        packed = np.empty(nb.value, np.uint8)
+        tail = np.empty(nt.value, np.uint32)
+        self._ck(self.lib.harcgpu_get_packed_order(self.h, _ptr(packed), _ptr(tail), None, None))
+        return packed, tail
 
     # ---- process contract
     def reorder_dir(self, basedir):

@@ -414,6 +414,18 @@ int harcgpu_get_globals(harcgpu_ctx *c, uint32_t *order, uint32_t *order_N, uint
 	return 0;
 }
 
+// pack_order.cpp:20-77 (harc:111-112, the -p mode) on the order stream of the last harcgpu_encode
+int harcgpu_get_packed_order(harcgpu_ctx *c, void *packed, uint32_t *tail, uint64_t *packed_bytes, uint32_t *tail_entries)
+{
+	if (!c || !c->encoded) { harcgpu_set_error("encode first"); return -1; }
+	CK(cudaSetDevice(c->device));
+	u64 pb = 0; u32 nt = 0;
+	int rc = s2_pack_order(c, packed, tail, &pb, &nt);
+	if (packed_bytes) *packed_bytes = pb;
+	if (tail_entries) *tail_entries = nt;
+	return rc;
+}
+
 // ---- the process contract (reorder.out / encoder.out) -------------------------------------------------------
 static bool slurp(const std::string &path, std::vector<char> &out)
 {

@@ -168,3 +168,4 @@ int s2_load_pool(harcgpu_ctx *c, const char *s_ascii, const u32 *order_s, u32 n_
 int s2_load_pool_dev(harcgpu_ctx *c, const void *d_N_ascii, u32 n_N);
 int s2_load_pool_ids(harcgpu_ctx *c, const u32 *ids, u32 n_s, const char *N_ascii, u32 n_N);
 int s2_encode(harcgpu_ctx *c);
+int s2_pack_order(harcgpu_ctx *c, void *h_packed, u32 *h_tail, u64 *packed_bytes, u32 *ntail);

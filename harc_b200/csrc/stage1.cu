@@ -15,12 +15,19 @@
 namespace {
 constexpr int PACK_RPB = 64; // reads per block: 64*(L+1) bytes is a multiple of 16 for every L
 
-__device__ __forceinline__ u32 code2_of(unsigned char ch)
+// 4 ASCII bases in a u32 -> their four 2-bit codes in 8 bits (base 0 in bits 0-1).  (ch >> 1) & 3 is A0 C1 T2 G3; the
+// reference's code (reorder.cpp:188-195) is A0 G1 C2 T3 = ((b0 ^ b1) << 1) | b1 of those two bits.
+__device__ __forceinline__ u32 squeeze4(u32 v) // one 2-bit field per byte -> 8 contiguous bits
 {
-	// (ch>>1)&3: A->0 C->1 T->2 G->3; reference code (reorder.cpp:188-195): A=0 G=1 C=2 T=3
-	return (0x78u >> (2 * ((ch >> 1) & 3))) & 3u;
+	return (v | (v >> 6) | (v >> 12) | (v >> 18)) & 0xffu;
 }
-// One block stages 64 lines in shared memory with 16-byte loads, then one thread per output word packs it.
+__device__ __forceinline__ u32 codes4(u32 w)
+{
+	const u32 b0 = (w >> 1) & 0x01010101u, b1 = (w >> 2) & 0x01010101u;
+	return ((b0 ^ b1) << 1) | b1;
+}
+// One block stages 64 lines in shared memory with 16-byte loads, then one thread per output word packs its 32 bases
+// four at a time from aligned 32-bit shared-memory words (funnel shift for the line's byte offset).
 // WITH_N (stage II pool, encoder.cpp:731-745): 'N' is stored as code 0 and flagged in a second word array at the
 // low bit of the base's pair; the reference's 3-bit code is then 2*code2 + nflag.
 template <bool WITH_N>
@@ -29,6 +36,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const char *__restrict__ asci
 {
 	extern __shared__ uint4 stage4[];
 	char *stage = reinterpret_cast<char *>(stage4);
+	const u32 *stage32 = reinterpret_cast<const u32 *>(stage4);
 	const size_t line = (size_t)L + 1;
 	const size_t r0 = (size_t)blockIdx.x * PACK_RPB;
 	const u32 nr = (u32)min((size_t)PACK_RPB, (size_t)n - r0);
@@ -40,19 +48,28 @@ __global__ void __launch_bounds__(256) pack_kernel(const char *__restrict__ asci
 	for (size_t b = nvec * 16 + threadIdx.x; b < bytes; b += blockDim.x) stage[b] = src[b];
 	__syncthreads();
 	for (u32 w = threadIdx.x; w < nr * (u32)NWo; w += blockDim.x) {
-		u32 r = w / NWo, k = w % NWo;
-		const unsigned char *s = reinterpret_cast<const unsigned char *>(stage + (size_t)r * line);
+		const u32 r = w / NWo, k = w % NWo;
+		const u32 o = r * (u32)line + 32 * k; // byte offset of the word's first base
+		const u32 q = o >> 2, sh = (o & 3u) * 8;
+		const int nb = min(32, L - 32 * (int)k); // bases in this word
 		u64 v = 0, vn = 0;
-		int b0 = k * 32;
-#pragma unroll 8
-		for (int c = 0; c < 32; c++)
-			if (b0 + c < L) {
-				unsigned char ch = s[b0 + c];
-				if (WITH_N && ch == 'N') vn |= 1ull << (2 * c);
-				else v |= (u64)code2_of(ch) << (2 * c);
+		u32 lo = stage32[q];
+#pragma unroll
+		for (int i = 0; i < 8; i++) {
+			const u32 hi = stage32[q + i + 1]; // the staging area has 32 bytes of slack
+			const u32 ch = __funnelshift_r(lo, hi, sh);
+			lo = hi;
+			u32 c = codes4(ch);
+			if (WITH_N) {
+				const u32 isn = __vcmpeq4(ch, 0x4E4E4E4Eu); // 0xff where the base is 'N'
+				c &= ~isn;
+				vn |= (u64)squeeze4(isn & 0x01010101u) << (8 * i);
 			}
-		out[(r0 + r) * NWo + k] = v;
-		if (WITH_N) outN[(r0 + r) * NWo + k] = vn;
+			v |= (u64)squeeze4(c) << (8 * i);
+		}
+		const u64 m = lowmask(2 * nb);
+		out[(r0 + r) * NWo + k] = v & m;
+		if (WITH_N) outN[(r0 + r) * NWo + k] = vn & m;
 	}
 }
 
@@ -153,7 +170,7 @@ int s1_pack_reads(harcgpu_ctx *c, const void *d_ascii, u32 n)
 {
 	if (n == 0) return 0;
 	size_t smem = (size_t)PACK_RPB * (c->L + 1);
-	smem = (smem + 15) / 16 * 16;
+	smem = (smem + 15) / 16 * 16 + 48; // slack: the last word of the last line reads up to 35 bytes past its start
 	pack_kernel<false><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, c->reads, nullptr);
 	CK(cudaGetLastError());
 	return 0;
@@ -163,7 +180,7 @@ int s1_packN(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *out2, u64 *outN)
 {
 	if (n == 0) return 0;
 	size_t smem = (size_t)PACK_RPB * (c->L + 1);
-	smem = (smem + 15) / 16 * 16;
+	smem = (smem + 15) / 16 * 16 + 48; // slack: the last word of the last line reads up to 35 bytes past its start
 	if (outN) pack_kernel<true><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, out2, outN);
 	else pack_kernel<false><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, out2, nullptr);
 	CK(cudaGetLastError());

@@ -16,6 +16,7 @@
 // Known deviation (documented in DESIGN.md): a pool dictionary bin with more than maxsearch (1000) live reads is
 // scanned over its top 1000 ids only, without tracking removals; the result is still lossless.
 #include "ctx.h"
+#include <string.h>
 #include <cub/device/device_radix_sort.cuh>
 
 namespace {
@@ -467,6 +468,26 @@ __global__ void __launch_bounds__(256) unaligned_N_kernel(const u64 *__restrict_
 	out[b] = ch;
 }
 
+// ---------------------------------------------------------------------------------------------- pack_order (pack_order.cpp:20-77)
+// Blocks of 32 entries, `numbits` bits each, as one little-endian bit stream of `numbits` u32 words per block.
+// One thread per output word: word k of a block holds bits [32k, 32k+32) of the block's stream.
+__global__ void __launch_bounds__(256) pack_order_kernel(const u32 *__restrict__ order, u64 nwords, int numbits, u32 *__restrict__ out)
+{
+	const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= nwords) return;
+	const u64 blk = t / numbits;
+	const int k = (int)(t % numbits);
+	const u32 *o = order + blk * 32;
+	const int b0 = 32 * k, b1 = b0 + 32; // bit range of this word
+	u32 v = 0;
+	for (int j = b0 / numbits; j < 32 && j * numbits < b1; j++) {
+		const int sh = j * numbits - b0;
+		const u32 x = __ldg(&o[j]);
+		v |= sh >= 0 ? x << sh : x >> (-sh);
+	}
+	out[t] = v;
+}
+
 // ---------------------------------------------------------------------------------------------- hand-off from stage I
 template <int NW>
 __global__ void __launch_bounds__(128) gather_stream_kernel(const u64 *__restrict__ reads, const u32 *__restrict__ order, const u8 *__restrict__ rev,
@@ -891,5 +912,33 @@ int s2_encode(harcgpu_ctx *c)
 	                f_src, f_kind, f_col, nm1, noff, revc, isN, exN, ordv, uf, exU, ulist, d_tail };
 	for (void *q : tmp) c->release(q);
 	c->encoded = true;
+	return 0;
+}
+
+// pack_order.cpp:20-77 on the order stream of the last encode: header {int numbits, u32 numreads}, packed blocks, tail
+int s2_pack_order(harcgpu_ctx *c, void *h_packed, u32 *h_tail, u64 *packed_bytes, u32 *ntail)
+{
+	const u32 n = c->esz.n_order;
+	const int numbits = n ? 32 - __builtin_clz(n) : 0; // (int)(log2(n) + 1)
+	const u64 nblk = n / 32, nwords = nblk * (u64)numbits;
+	if (packed_bytes) *packed_bytes = 8 + 4 * nwords;
+	if (ntail) *ntail = n % 32;
+	if (h_packed) {
+		int hdr[2] = { numbits, (int)n };
+		memcpy(h_packed, hdr, 8);
+		if (nwords) {
+			u32 *d = nullptr;
+			if (c->alloc(&d, nwords)) return -1;
+			pack_order_kernel<<<KL + cdiv(nwords, 256), 256, 0, c->st>>>(c->o_order, nwords, numbits, d);
+			CK(cudaGetLastError());
+			CK(cudaMemcpyAsync((char *)h_packed + 8, d, 4 * nwords, cudaMemcpyDeviceToHost, c->st));
+			CK(cudaStreamSynchronize(c->st));
+			c->release(d);
+		}
+	}
+	if (h_tail && n % 32) {
+		CK(cudaMemcpyAsync(h_tail, c->o_order + nblk * 32, 4 * (size_t)(n % 32), cudaMemcpyDeviceToHost, c->st));
+		CK(cudaStreamSynchronize(c->st));
+	}
 	return 0;
 }

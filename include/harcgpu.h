@@ -127,6 +127,11 @@ int harcgpu_get_set(harcgpu_ctx *ctx, int k, uint8_t *seq, char *seq_tail, uint8
 int harcgpu_get_globals(harcgpu_ctx *ctx, uint32_t *order, uint32_t *order_N, uint8_t *singleton,
                         char *singleton_tail, char *input_N);
 
+/* pack_order.cpp:20-77 (run by harc:111-112 in the order-preserving mode -p) on the read_order.bin stream of the last
+ * harcgpu_encode: `packed` receives the new read_order.bin (header {int numbits; uint32 numreads}, then numbits u32 words
+ * per block of 32 entries), `tail` the read_order.bin.tail entries.  With NULL buffers only the sizes are written. */
+int harcgpu_get_packed_order(harcgpu_ctx *ctx, void *packed, uint32_t *tail, uint64_t *packed_bytes, uint32_t *tail_entries);
+
 /* ---- one job on several GPUs of one box (one process and one context per GPU) -------------------------------
  * Not in the reference (it is one process).  Every GPU holds all packed reads and both dictionaries; what is shared is
  * the claimed-read bitmap (reorder.cpp:449 remainingreads + the lock arrays of reorder.cpp:436-442): it is cut into

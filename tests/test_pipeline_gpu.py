@@ -68,8 +68,11 @@ def test_order_preserving_round_trip(workroot, L, K, n, G):
     ctx = harc_b200.HarcGpu(L, walkers=0, file_sets=K)
     ctx.reorder_dir(d)
     ctx.encode_dir(d)
+    packed, tail = ctx.get_packed_order()      # pack_order.cpp on the GPU (harc:111-112)
     ctx.close()
-    R.pack_order(d)
+    R.pack_order(d)                            # the reference's own pack_order.out, in place
+    assert packed.tobytes() == open(os.path.join(d, "output", "read_order.bin"), "rb").read()
+    assert tail.tobytes() == open(os.path.join(d, "output", "read_order.bin.tail"), "rb").read()
     R.decoder_preserve(d, L)
     fq = np.fromfile(os.path.join(d, "r.fastq"), dtype=np.uint8).tobytes().split(b"\n")[1::4]
     got = open(os.path.join(d, "output", "output.dna"), "rb").read()
