@@ -80,6 +80,18 @@ struct alignas(16) WalkerSmem {
 	u32 pad_[3];
 };
 
+#ifdef WALK_PROF
+// tuning aid (build with HARC_CUFLAGS=-DWALK_PROF): warp cycles per region of the walk, summed over all warps
+__device__ unsigned long long g_walk_prof[16];
+#define PROF_T0() long long pt_ = clock64()
+#define PROF_ADD(i) do { long long t_ = clock64(); if (lane == 0) pacc[i] += (u64)(t_ - pt_); pt_ = t_; } while (0)
+#define PROF_CNT(i, v) do { if (lane == 0) pacc[i] += (u64)(v); } while (0)
+#else
+#define PROF_T0()
+#define PROF_ADD(i)
+#define PROF_CNT(i, v)
+#endif
+
 __device__ __forceinline__ u32 ldvol(const u32 *p) { return *((const volatile u32 *)p); }
 
 template <int NW>
@@ -246,6 +258,11 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 	const int L = a.L;
 
 	u32 c_steps = 0, c_probes = 0, c_hits = 0, c_cmp = 0, c_fail = 0, c_restart = 0;
+#ifdef WALK_PROF
+	u64 pacc[16];
+	for (int i = 0; i < 16; i++) pacc[i] = 0;
+	const long long pstart_ = clock64();
+#endif
 
 	// forward log (leader only)
 	auto emit = [&](u64 rec) {
@@ -301,6 +318,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 
 	while (true) {
 		if (!__any_sync(FULL, state != S_DONE)) break;
+		PROF_T0();
 
 		// ---- new chain head (reorder.cpp:650-688).  The reference takes the highest unclaimed index through a private
 		// downward cursor per thread.  Here the reads are cut into one stripe per walker; a walker scans its own stripe
@@ -365,6 +383,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 			}
 		}
 
+		PROF_ADD(0);
 		// ---- start a chain at `current`: the window is the read itself (reorder.cpp:875-883); with the left extension the
 		// walk starts on the reverse-complement strand
 		if (__any_sync(FULL, state == S_NEWHEAD)) {
@@ -381,6 +400,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 			}
 		}
 
+		PROF_ADD(1);
 		// ---- search round: the four probe kinds of SPR * U consecutive shifts.  Every lane first issues its U slot loads
 		// (independent, so their latencies overlap), then the hits are worked off in shift order.
 		const bool searching = state == S_SEARCH;
@@ -416,6 +436,9 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 				}
 			}
 			c_steps += leader && searching && jb == 0;
+			PROF_ADD(2);
+			PROF_CNT(8, searching);
+			PROF_CNT(9, searching && jb == 0);
 #pragma unroll
 			for (int u = 0; u < UX; u++) {
 				if (!__any_sync(FULL, bsize[u] != 0u && !found)) continue;
@@ -468,6 +491,8 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 			}
 		}
 
+		PROF_ADD(3);
+		PROF_CNT(10, found);
 		// ---- a read was appended (reorder.cpp:560-578 / 624-641)
 		if (__any_sync(FULL, found)) {
 			if (found) {
@@ -497,6 +522,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 			if (jb >= a.maxmatch) state = S_CHAINEND;
 		}
 
+		PROF_ADD(4);
 		// ---- nothing matches the window any more
 		if (__any_sync(FULL, state == S_CHAINEND)) {
 			if (state == S_CHAINEND) {
@@ -540,7 +566,17 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 				}
 			}
 		}
+		PROF_ADD(5);
 	}
+#ifdef WALK_PROF
+	if (lane == 0) {
+		for (int i = 0; i < 11; i++) atomicAdd(&g_walk_prof[i], pacc[i]);
+		const u64 life = (u64)(clock64() - pstart_);
+		atomicAdd(&g_walk_prof[11], life);
+		atomicMax(&g_walk_prof[12], life);
+		atomicAdd(&g_walk_prof[13], 1ull);
+	}
+#endif
 	// counters
 	for (int o = 16; o > 0; o >>= 1) {
 		c_steps += __shfl_xor_sync(FULL, c_steps, o);
@@ -751,6 +787,16 @@ int s1_reorder(harcgpu_ctx *c)
 	if (rc) return rc;
 	c->toc("walk");
 	CK(cudaGetLastError());
+#ifdef WALK_PROF
+	{
+		unsigned long long h[16], z[16] = { 0 };
+		CK(cudaStreamSynchronize(st));
+		CK(cudaMemcpyFromSymbol(h, g_walk_prof, sizeof h));
+		CK(cudaMemcpyToSymbol(g_walk_prof, z, sizeof z));
+		fprintf(stderr, "WALK_PROF walkers %u cycles: restart %llu newhead %llu probe %llu cand %llu append %llu chainend %llu | rounds %llu steps %llu found %llu | warp life avg %llu max %llu warps %llu\n",
+		        walkers, h[0], h[1], h[2], h[3], h[4], h[5], h[8], h[9], h[10], h[13] ? h[11] / h[13] : 0ull, h[12], h[13]);
+	}
+#endif
 
 	// ---- finalize
 	c->tic();
