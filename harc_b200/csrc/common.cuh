@@ -49,7 +49,7 @@ __device__ __forceinline__ u32 slot_hash(u64 x)
 }
 
 // One dictionary: canonical CSR (keys ascending, ids ascending inside a bin: reorder.cpp:344-391) plus an
-// open-addressing table key -> bin.  A slot is 16 bytes {key, val}: val == 0 = empty, else size = val >> 32 and the low
+// open-addressing table key -> bin.  A slot is 16 bytes {key, val}: val == 0 = empty, else size = bits 32..62 and the low
 // half is the bin's first index into ids[] -- or, for a bin of one read (most bins), the read id itself, so that the
 // common probe needs no second dependent load.
 struct DictDev {
@@ -68,16 +68,32 @@ struct DictView {
 	int dstart, dend; // in bases
 };
 
-// Slots are probed in buckets of two (one 32-byte sector): a key hashes to an even slot and is inserted into the first
-// empty slot from there on, so a lookup reads both slots of a bucket at once and stops at the first empty one.
+// Slots are probed in buckets of two (one 32-byte sector): a key hashes to an even slot (its home bucket) and is inserted
+// into the first empty slot from there on.  A key that did not fit into its home bucket sets the OVERFLOW bit (bit 63 of
+// val) of the home bucket's first slot, so a lookup that misses in the home bucket only goes on when that bit is set:
+// ~95 % of all lookups, present or absent, end after one 32-byte load.
+// val = overflow << 63 | size << 32 | lo; size == 0 <=> empty slot.
+constexpr u64 SLOT_OVERFLOW = 1ull << 63;
+__device__ __forceinline__ u32 slot_size(u64 val) { return (u32)(val >> 32) & 0x7fffffffu; }
+
+// One step of a lookup over the bucket (s0, s1); `home` = this is the key's home bucket.
+// returns 1: found (lo, size set), 0: absent, 2: go on with the next bucket
+__device__ __forceinline__ int bucket_step(u64 key, ulonglong2 s0, ulonglong2 s1, bool home, u32 &lo, u32 &size)
+{
+	const u32 z0 = slot_size(s0.y), z1 = slot_size(s1.y);
+	if (z0 != 0u && s0.x == key) { lo = (u32)s0.y; size = z0; return 1; }
+	if (z0 != 0u && z1 != 0u && s1.x == key) { lo = (u32)s1.y; size = z1; return 1; }
+	if (home) return (s0.y & SLOT_OVERFLOW) ? 2 : 0;
+	return (z0 != 0u && z1 != 0u) ? 2 : 0;
+}
 // true if the key is present: size = reads in the bin, lo = first index into ids[] (size > 1) or the read id (size == 1)
 __device__ __forceinline__ bool dict_resolve(const DictView &d, u64 key, u32 h, ulonglong2 s0, ulonglong2 s1, u32 &lo, u32 &size)
 {
+	bool home = true;
 	while (true) {
-		if ((u32)(s0.y >> 32) == 0u) return false;
-		if (s0.x == key) { lo = (u32)s0.y; size = (u32)(s0.y >> 32); return true; }
-		if ((u32)(s1.y >> 32) == 0u) return false;
-		if (s1.x == key) { lo = (u32)s1.y; size = (u32)(s1.y >> 32); return true; }
+		const int r = bucket_step(key, s0, s1, home, lo, size);
+		if (r != 2) return r == 1;
+		home = false;
 		h = (h + 2) & d.slot_mask;
 		s0 = __ldg(&d.slots[h]);
 		s1 = __ldg(&d.slots[h + 1]);

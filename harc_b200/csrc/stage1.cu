@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(256) bins_kernel(const u64 *__restrict__ ks, c
 	start[b] = i;
 }
 
-// One thread per bin: linear probing, CAS on the val half of the slot; the table is read-only afterwards.
+// One thread per bin: linear probing, CAS on the val half of the slot; the table is read-only afterwards.  A bin that lands
+// outside its home bucket raises the home bucket's overflow bit (common.cuh: bucket_step).
 __global__ void __launch_bounds__(256) insert_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ start, const u32 *__restrict__ ids,
                                                      u32 numkeys, ulonglong2 *slots, u32 mask)
 {
@@ -157,10 +158,16 @@ __global__ void __launch_bounds__(256) insert_kernel(const u64 *__restrict__ key
 	u64 key = keys[b];
 	u32 s = start[b], sz = start[b + 1] - s;
 	u64 val = (u64)(sz == 1 ? ids[s] : s) | ((u64)sz << 32);
-	u32 h = slot_hash(key) & mask & ~1u; // buckets of two slots (common.cuh: dict_resolve)
+	const u32 h0 = slot_hash(key) & mask & ~1u; // buckets of two slots
+	u32 h = h0;
 	while (true) {
 		u64 old = atomicCAS(&slots[h].y, 0ull, val);
-		if (old == 0ull) { slots[h].x = key; return; }
+		if (old == 0ull) {
+			slots[h].x = key;
+			// the home bucket was full (both CAS failed on non-zero words), so the bit never lands on an empty slot
+			if ((h & ~1u) != h0) atomicOr(&slots[h0].y, SLOT_OVERFLOW);
+			return;
+		}
 		h = (h + 1) & mask;
 	}
 }

@@ -1,12 +1,14 @@
 // Stage I chain walk of HARC (reference: reorder.cpp:434-703 reorder(), 863-915 updaterefcount) as one sm_100a kernel.
 //
-// A walker is the reference's OpenMP thread: it follows one chain of overlapping reads at a time.  Here a walker is a
-// group of G = 8 lanes, four walkers per warp, thousands per GPU.  Per round the 8 lanes of a walker issue the
-// reference's four probe kinds (forward dict 0, forward dict 1, reverse dict 0, reverse dict 1) for eight consecutive
-// shifts (four independent probes per lane); the lowest lane with a claimable candidate wins, which is exactly the sequential order of
-// reorder.cpp:517-649, so one walker reproduces the reference at num_thr=1 byte for byte.  Reads are claimed with one
-// atomicAnd on a bitmap (instead of the reference's 2 x 2^24 striped locks and its in-place bin compaction); the
-// consensus window of updaterefcount lives in shared memory as a circular array of vote counts.
+// A walker is the reference's OpenMP thread: it follows one chain of overlapping reads at a time.  Here a walker is one
+// warp, thousands per GPU.  Per round the 32 lanes issue the reference's four probe kinds (forward dict 0, forward
+// dict 1, reverse dict 0, reverse dict 1) for eight consecutive shifts, lane = 4 * shift + kind; the lowest lane with a
+// claimable candidate wins, which is exactly the sequential order of reorder.cpp:517-649, so one walker reproduces the
+// reference at num_thr=1 byte for byte.  Reads are claimed with one atomicAnd on a bitmap (instead of the reference's
+// 2 x 2^24 striped locks and its in-place bin compaction); the consensus window of updaterefcount lives in shared
+// memory as a circular array of vote keys.  Everything on the hot path works on 32-bit words (funnel shifts over
+// zero-padded shared-memory arrays, compare masks from a per-block table), because the kernel is bound by instruction
+// issue and dependent latency, not by bandwidth (profiles/).
 //
 // Not in the reference (switchable, params.extend): a new chain is first extended to the LEFT of its head by walking the
 // reverse-complement strand, and that run is written in front of the head in reverse order.  The streams only encode
@@ -19,14 +21,15 @@
 #include <cub/device/device_radix_sort.cuh>
 
 namespace {
-// A walker is a group of G lanes (G = 8, 16 or 32: template parameter), 32/G walkers per warp.  Per round a walker issues
-// 32 probes: the four probe kinds of 8 consecutive shifts, i.e. U = 32/G independent probes per lane.
-constexpr int WALK_WARPS = 4;         // warps per block
+constexpr int WALK_WARPS = 4;         // warps (= walkers) per block
 constexpr int CHUNK = 32;             // records per log chunk
+constexpr int SPR = 8;                // shifts probed per round
 constexpr u32 NONE = 0xffffffffu;
 constexpr u32 FULL = 0xffffffffu;
+constexpr int DRY_HEADS = 4;          // left extension is skipped after this many heads in a row that stayed alone
 
 enum { S_SEARCH = 0, S_CHAINEND, S_RESTART, S_NEWHEAD, S_DONE };
+enum { P_DEAD = 0, P_PENDING, P_BIN, P_CAND };
 
 // record: rid | pos<<32 | rev<<40 | matched<<41 | singleton<<42
 __device__ __forceinline__ u64 mkrec(u32 rid, u32 pos, u32 rev, u32 matched, u32 single)
@@ -65,19 +68,23 @@ struct WalkArgs {
 	u64 *counters;
 };
 
+// Per-walker shared memory.  ref / rref / cur are arrays of 32-bit words with zero words around them, so that a window
+// moved by any shift is read without bounds checks: forward windows read up to NW words above ref, reverse windows up
+// to NW words below rref (the same zeros), key extraction up to two words above either.
 template <int NW>
 struct alignas(16) WalkerSmem {
-	u32 key[4 * 32 * NW]; // vote keys (count << 2 | tie rank) per base code and window position, circular (see update_ref)
-	u32 best[32 * NW];    // the largest of the four keys of a position
-	u64 ref[NW];          // consensus of the current window, 2 bits/base (reorder.cpp:466)
-	u64 rref[NW];         // its reverse complement
-	u64 cur[NW];          // the read just appended
+	uint4 key[32 * NW];   // vote keys (count << 2 | tie rank) of the four base codes per window position, circular (update_ref)
 	long long cursor;     // restart: downward cursor inside the current stripe
 	u32 stripe, stripes_tried;
 	u32 chunk, fill, seq;                      // forward log
 	u32 lchunk, lfill, lfirst, lcount, j1;     // left log
 	u32 pend, pend_f;                          // left run: read found last, not yet written
-	u32 pad_[3];
+	u32 ref[2 * NW];      // consensus of the current window, 2 bits/base (reorder.cpp:466)
+	u32 zpad[NW];
+	u32 rref[2 * NW];     // its reverse complement
+	u32 zpad2[2];
+	u32 cur[2 * NW];      // the read just appended
+	u32 zpad3[2];
 };
 
 #ifdef WALK_PROF
@@ -95,126 +102,116 @@ __device__ unsigned long long g_walk_prof[16];
 __device__ __forceinline__ u32 ldvol(const u32 *p) { return *((const volatile u32 *)p); }
 
 template <int NW>
-__device__ __forceinline__ void load_read(const u64 *__restrict__ reads, u32 rid, u64 (&rw)[NW])
+__device__ __forceinline__ void load_read(const u64 *__restrict__ reads, u32 rid, u32 (&rw)[2 * NW])
 {
 	const u64 *r = reads + (size_t)rid * NW;
 	if (NW % 2 == 0) {
-		const ulonglong2 *r2 = reinterpret_cast<const ulonglong2 *>(r);
+		const uint4 *r4 = reinterpret_cast<const uint4 *>(r);
 #pragma unroll
-		for (int k = 0; k < NW / 2; k++) { ulonglong2 v = __ldg(&r2[k]); rw[2 * k] = v.x; rw[2 * k + 1] = v.y; }
+		for (int k = 0; k < NW / 2; k++) { uint4 v = __ldg(&r4[k]); rw[4 * k] = v.x; rw[4 * k + 1] = v.y; rw[4 * k + 2] = v.z; rw[4 * k + 3] = v.w; }
 	} else {
+		const uint2 *r2 = reinterpret_cast<const uint2 *>(r);
 #pragma unroll
-		for (int k = 0; k < NW; k++) rw[k] = __ldg(&r[k]);
+		for (int k = 0; k < NW; k++) { uint2 v = __ldg(&r2[k]); rw[2 * k] = v.x; rw[2 * k + 1] = v.y; }
 	}
 }
 
-__device__ __forceinline__ u64 revpairs64_w(u64 x) // reverse the order of the 32 base pairs of a word
+__device__ __forceinline__ u32 revpairs32(u32 x) // reverse the order of the 16 base pairs of a word
 {
-	u64 y = __brevll(x);
-	return ((y & 0x5555555555555555ull) << 1) | ((y >> 1) & 0x5555555555555555ull);
+	const u32 y = __brev(x);
+	return ((y & 0x55555555u) << 1) | ((y >> 1) & 0x55555555u);
 }
+__device__ __forceinline__ u32 lowmask32(int n) { return n >= 32 ? ~0u : (n <= 0 ? 0u : ((1u << n) - 1u)); }
 
-// bits [pos, pos+n) of a little-endian word array with zero fill outside [0, 64*words); pos may be negative, n <= 64
-__device__ __forceinline__ u64 getbits_z(const u64 *w, int words, int pos, int n)
+// updaterefcount (reorder.cpp:863-915) for one walker, by the 32 lanes of its warp.
+// Lane `lane` owns the B = NW consecutive window positions [B*lane, B*lane+B).  The votes of a position are four keys
+// (count << 2 | tie rank), one per base code (bit-code order A, G, C, T), in one uint4: a read adds one vote per
+// position, and argmax with ties -> A < C < G < T (strict '>' from max = 0, reorder.cpp:893-899) is the tie rank in
+// the low bits of the largest key.  The window is circular (origin `head`) over LP = 32*NW slots so that a shift
+// moves no data; slot p lives at index (p % B) * 32 + p / B, which makes the lanes touch 32 consecutive uint4.
+template <int NW>
+__device__ __forceinline__ void update_ref(WalkerSmem<NW> &s, int L, int lane, bool reset, bool rev, int shift, int &head)
 {
-	const int q = pos >> 6, r = pos & 63; // arithmetic shift: floor division also for negative pos
-	const u64 lo = (q >= 0 && q < words) ? w[q] : 0ull;
-	const u64 hi = (q + 1 >= 0 && q + 1 < words) ? w[q + 1] : 0ull;
-	u64 v = r ? (lo >> r) | (hi << (64 - r)) : lo;
-	if (n < 64) v &= (1ull << n) - 1;
-	return v;
-}
-
-// updaterefcount (reorder.cpp:863-915) for one walker, by its G lanes.
-// Lane `sub` owns the B = 32*NW/G consecutive window positions [B*sub, B*sub+B).  Votes are kept as keys
-// (count << 2 | tie rank), one array per base code, plus the largest key of every position: a read adds one vote per
-// position, so only the voted key and the maximum change (one 4-byte read-modify-write each), and argmax with ties
-// -> A < C < G < T (strict '>' from max = 0, reorder.cpp:893-899) is the tie rank in the low bits of the maximum.
-// The window is circular (origin `head`) over LP = 32*NW slots so that a shift moves no data; slot p lives at index
-// (p % B) * G + p / B, which makes the G lanes of a walker touch G consecutive words (no bank conflicts).
-template <int NW, int G>
-__device__ __forceinline__ void update_ref(WalkerSmem<NW> &s, int L, int sub, u32 gmask, bool reset, bool rev, int shift, int &head)
-{
-	constexpr int B = 32 * NW / G, LP = 32 * NW;
+	constexpr int B = NW, LP = 32 * NW, W2 = 2 * NW;
 	if (reset) head = 0;
 	else { head += shift; if (head >= LP) head -= LP; }
 	// the 2B bits of the new read that fall on this lane's positions (reverse-complemented first if rev)
-	u64 mine;
-	if (!rev) mine = getbits_z(s.cur, NW, 2 * B * sub, 2 * B);
-	else {
-		u64 v = getbits_z(s.cur, NW, 2 * (L - B * sub - B), 2 * B);
-		mine = (revpairs64_w(v) >> (64 - 2 * B)) ^ lowmask(2 * B);
+	u32 mine;
+	{
+		const int pos = rev ? 2 * (L - B * lane - B) : 2 * B * lane; // >= -64: the words below cur are padding
+		const int q = pos >> 5, r = pos & 31;
+		const u32 v = __funnelshift_r(s.cur[q], s.cur[q + 1], r);
+		mine = rev ? (revpairs32(v << (32 - 2 * B)) ^ lowmask32(2 * B)) : v;
 	}
 	int q = head / B, r = head % B;
 	const int fresh = reset ? 0 : L - shift; // positions >= fresh enter the window with this read (reorder.cpp:903-908)
-	u64 out = 0;
+	u32 out = 0;
 #pragma unroll
 	for (int t = 0; t < B; t++) {
-		const int i = B * sub + t;
-		const int idx = r * G + ((sub + q) & (G - 1));
-		const u32 cc = (u32)(mine >> (2 * t)) & 3u;
-		// one vote: only the voted key and the maximum of the position change; a position that enters the window
-		// (i >= fresh) starts from the bare tie ranks of A, G, C, T (bit-code order): 3, 1, 2, 0
-		const bool inl = i < L, isfresh = i >= fresh;
-		u32 k = s.key[cc * LP + idx], b = s.best[idx];
-		if (isfresh) { k = (0x27u >> (2 * cc)) & 3u; b = 0u; }
-		k += 4u;
-		b = max(b, k);
-		if (isfresh && inl) { s.key[idx] = 3u; s.key[LP + idx] = 1u; s.key[2 * LP + idx] = 2u; s.key[3 * LP + idx] = 0u; }
-		if (inl) { s.key[cc * LP + idx] = k; s.best[idx] = b; }
+		const int i = B * lane + t;
+		const int idx = r * 32 + ((lane + q) & 31);
+		const u32 cc = (mine >> (2 * t)) & 3u;
+		uint4 v = s.key[idx];
+		// a position that enters the window starts from the bare tie ranks of A, G, C, T (bit-code order): 3, 1, 2, 0
+		if (i >= fresh) v = make_uint4(3u, 1u, 2u, 0u);
+		v.x += cc == 0u ? 4u : 0u;
+		v.y += cc == 1u ? 4u : 0u;
+		v.z += cc == 2u ? 4u : 0u;
+		v.w += cc == 3u ? 4u : 0u;
+		u32 b = max(max(v.x, v.y), max(v.z, v.w));
+		if (i < L) s.key[idx] = v;
 		else b = 3u; // beyond the read: base A, the zero bits of the reference's bitset
-		out |= (u64)((0x27u >> (2 * (b & 3u))) & 3u) << (2 * t); // tie rank 3,2,1,0 -> code A0 C2 G1 T3
+		out |= ((0x27u >> (2 * (b & 3u))) & 3u) << (2 * t); // tie rank 3,2,1,0 -> code A0 C2 G1 T3
 		if (++r == B) { r = 0; q++; }
 	}
 	if ((2 * B) % 8 == 0) {
-		unsigned char *rb = reinterpret_cast<unsigned char *>(s.ref) + (2 * B / 8) * sub;
+		unsigned char *rb = reinterpret_cast<unsigned char *>(s.ref) + (2 * B / 8) * lane;
 		if (2 * B == 8) *rb = (unsigned char)out;
-		else if (2 * B == 16) *reinterpret_cast<unsigned short *>(rb) = (unsigned short)out;
-		else if (2 * B == 32) *reinterpret_cast<u32 *>(rb) = (u32)out;
-		else if (2 * B == 64) *reinterpret_cast<u64 *>(rb) = out;
-		else {
-#pragma unroll
-			for (int k = 0; k < 2 * B / 8; k++) rb[k] = (unsigned char)(out >> (8 * k));
-		}
-		__syncwarp(gmask);
-	} else { // pieces that are not whole bytes (2B <= 28 bits here) are OR-ed into the zeroed words
-		if (sub < NW) s.ref[sub] = 0ull;
-		__syncwarp(gmask);
-		u32 *r32 = reinterpret_cast<u32 *>(s.ref);
-		const int o = 2 * B * sub, w = o >> 5, sh = o & 31;
-		atomicOr(&r32[w], (u32)out << sh);
-		if (sh + 2 * B > 32) atomicOr(&r32[w + 1], (u32)out >> (32 - sh));
-		__syncwarp(gmask);
+		else *reinterpret_cast<unsigned short *>(rb) = (unsigned short)out; // 2 * B == 16
+		__syncwarp();
+	} else { // pieces that are not whole bytes (2B <= 14 bits here) are OR-ed into the zeroed words
+		if (lane < W2) s.ref[lane] = 0u;
+		__syncwarp();
+		const int o = 2 * B * lane, w = o >> 5, sh = o & 31;
+		atomicOr(&s.ref[w], out << sh);
+		if (sh + 2 * B > 32) atomicOr(&s.ref[w + 1], out >> (32 - sh));
+		__syncwarp();
 	}
-	if (sub < NW) {
-		const int sft = 2 * (32 * NW - L);
-		const u64 t0 = revpairs64_w(s.ref[NW - 1 - sub]);
-		const u64 t1 = sub + 1 < NW ? revpairs64_w(s.ref[NW - 2 - sub]) : 0ull;
-		const u64 x = sft ? (t0 >> sft) | (t1 << (64 - sft)) : t0;
-		s.rref[sub] = x ^ lowmask(2 * L - 64 * sub);
+	if (lane < W2) {
+		// rref = (ref with its 32*NW base pairs in reverse order) >> (64*NW - 2L), valid bits complemented
+		const int sft = 64 * NW - 2 * L, so = sft >> 5, sr = sft & 31;
+		const int i0 = W2 - 1 - (lane + so), i1 = i0 - 1;
+		const u32 t0 = i0 >= 0 ? revpairs32(s.ref[i0]) : 0u;
+		const u32 t1 = i1 >= 0 ? revpairs32(s.ref[i1]) : 0u;
+		s.rref[lane] = __funnelshift_r(t0, t1, sr) ^ lowmask32(2 * L - 32 * lane);
 	}
-	__syncwarp(gmask);
+	__syncwarp();
 }
 
 // popcount(ref ^ (read & mask[j])) with ref >>= 2j (forward, reorder.cpp:543) or
 // popcount(revref ^ (read & revmask[j])) with revref <<= 2j (reverse, reorder.cpp:608).
-// One code path for both (forward and reverse lanes sit in the same warp): the window is the consensus moved by
-// off = +2j (ref) or -2j (rref) bits with zero fill, compared on the bits [mlo, mhi) that both reads cover.
+// One code path for both: `w` points at the word of ref (rref) that holds bit +2j (-2j, in the zero padding), r is
+// that offset modulo 32, and `m` is the row of the block's mask table with the bits both reads cover.
 template <int NW>
-__device__ __forceinline__ int hamming(const WalkerSmem<NW> &s, const u64 (&rw)[NW], int L, int j, bool rev)
+__device__ __forceinline__ int hamming(const u32 *w, int r, const u32 *m, const u32 (&rw)[2 * NW])
 {
-	const u64 *w = rev ? s.rref : s.ref;
-	const int off = rev ? -2 * j : 2 * j;
-	const int mlo = rev ? 2 * j : 0, mhi = rev ? 2 * L : 2 * (L - j);
-	const int q = off >> 6, r = off & 63; // floor division also for negative off
-	int d = 0;
-	u64 lo = (q >= 0 && q < NW) ? w[q] : 0ull;
+	u32 mk[2 * NW];
+	if (NW % 2 == 0) {
 #pragma unroll
-	for (int k = 0; k < NW; k++) {
-		const u64 hi = (k + q + 1 >= 0 && k + q + 1 < NW) ? w[k + q + 1] : 0ull;
-		const u64 x = r ? (lo >> r) | (hi << (64 - r)) : lo;
-		const u64 m = lowmask(mhi - 64 * k) & ~lowmask(mlo - 64 * k);
-		d += __popcll((x ^ rw[k]) & m);
+		for (int k = 0; k < NW / 2; k++) {
+			const uint4 v = reinterpret_cast<const uint4 *>(m)[k];
+			mk[4 * k] = v.x; mk[4 * k + 1] = v.y; mk[4 * k + 2] = v.z; mk[4 * k + 3] = v.w;
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < NW; k++) { const uint2 v = reinterpret_cast<const uint2 *>(m)[k]; mk[2 * k] = v.x; mk[2 * k + 1] = v.y; }
+	}
+	int d = 0;
+	u32 lo = w[0];
+#pragma unroll
+	for (int k = 0; k < 2 * NW; k++) {
+		const u32 hi = w[k + 1];
+		d += __popc((__funnelshift_r(lo, hi, r) ^ rw[k]) & mk[k]);
 		lo = hi;
 	}
 	return d;
@@ -241,21 +238,34 @@ __device__ __forceinline__ bool try_claim(const WalkArgs &a, u32 rid)
 	return (old & bit) != 0;
 }
 
-template <int NW, int G>
-__global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ? 2 : 1)) walk_kernel(WalkArgs a)
+// One dictionary probe in flight: the key and the bucket of two slots being looked at.
+struct Probe {
+	u64 key;
+	u32 h;
+	ulonglong2 s0, s1;
+	bool pend, home;
+};
+
+template <int NW>
+__global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? 8 : 4) walk_kernel(WalkArgs a)
 {
-	constexpr int WPW = 32 / G;  // walkers per warp
-	constexpr int SPR = G / 4;   // shifts covered by the lanes of a walker at once
-	constexpr int U = 32 / G;    // probes per lane per round: a round covers SPR * U = 8 shifts
-	constexpr int UX = G == 32 ? 2 : U; // one walker per warp: after a first round without a match the rounds are twice as wide
+	constexpr int W2 = 2 * NW;
 	extern __shared__ uint4 smem_raw[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int sub = lane & (G - 1), gbase = lane & ~(G - 1);
-	const u32 gmask = (G == 32 ? FULL : ((1u << (G & 31)) - 1u)) << gbase;
-	const bool leader = sub == 0;
-	const u32 wid = (blockIdx.x * WALK_WARPS + warp) * WPW + lane / G;
-	WalkerSmem<NW> &s = reinterpret_cast<WalkerSmem<NW> *>(smem_raw)[warp * WPW + lane / G];
+	const bool leader = lane == 0;
+	const u32 wid = blockIdx.x * WALK_WARPS + warp;
+	WalkerSmem<NW> &s = reinterpret_cast<WalkerSmem<NW> *>(smem_raw)[warp];
+	// compare masks, one row of W2 words per (direction, shift): forward bits [0, 2(L-j)), reverse bits [2j, 2L)
+	u32 *mtab = reinterpret_cast<u32 *>(smem_raw) + WALK_WARPS * (sizeof(WalkerSmem<NW>) / 4);
 	const int L = a.L;
+	for (int i = threadIdx.x; i < 2 * a.maxmatch * W2; i += WALK_WARPS * 32) {
+		const int row = i / W2, k = i % W2, rv = row >= a.maxmatch, j = rv ? row - a.maxmatch : row;
+		const int mlo = rv ? 2 * j : 0, mhi = rv ? 2 * L : 2 * (L - j);
+		mtab[i] = lowmask32(mhi - 32 * k) & ~lowmask32(mlo - 32 * k);
+	}
+	if (lane < NW) s.zpad[lane] = 0u;
+	if (lane < 2) { s.zpad2[lane] = 0u; s.zpad3[lane] = 0u; }
+	__syncthreads();
 
 	u32 c_steps = 0, c_probes = 0, c_hits = 0, c_cmp = 0, c_fail = 0, c_restart = 0;
 #ifdef WALK_PROF
@@ -289,7 +299,8 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 		a.lrecs[(size_t)s.lchunk * CHUNK + s.lfill++] = rec;
 	};
 
-	int state = S_DONE, head = 0, jb = 0;
+	// walker state: identical in all lanes of the warp (every update comes from a broadcast value)
+	int state = S_DONE, head = 0, jb = 0, dry = 0;
 	bool left_mode = false, prev_unmatched = false;
 	u32 current = 0, prev = 0;
 	if (leader) {
@@ -304,153 +315,176 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 		// here the walker looks for another head instead.)
 		const u32 start = a.base + (u32)((u64)wid * (a.n_loc / a.walkers));
 		int ok = leader ? (int)try_claim(a, start) : 0;
-		ok = __shfl_sync(gmask, ok, gbase);
+		ok = __shfl_sync(FULL, ok, 0);
 		if (ok) { current = start; state = S_NEWHEAD; c_restart += leader; }
 		else state = S_RESTART;
 	}
 
-	const int kind = sub & 3;   // 0: fwd dict0, 1: fwd dict1, 2: rev dict0, 3: rev dict1 (reorder.cpp:517-643 order)
+	// lane constants: probe kind and shift inside a round
+	const int kind = lane & 3;   // 0: fwd dict0, 1: fwd dict1, 2: rev dict0, 3: rev dict1 (reorder.cpp:517-643 order)
+	const int jq = lane >> 2;
 	const bool rev = kind >= 2;
 	const int l = kind & 1;
 	const bool dict_on = l < a.numdict;
 	const DictView dv = a.d[l];
 	const int kb = a.kbits[l];
+	const u32 kmlo = lowmask32(kb), kmhi = lowmask32(kb - 32);
+	const u32 *wbase = rev ? s.rref : s.ref;
+	const u32 *mbase = mtab + (rev ? a.maxmatch * W2 : 0);
 
-	while (true) {
-		if (!__any_sync(FULL, state != S_DONE)) break;
+	// issue the probe of this lane for shift j: key = the dictionary window of the consensus moved by j
+	auto issue = [&](int j, Probe &p) {
+		p.pend = dict_on && j < a.maxmatch && (rev ? dv.dstart > j : dv.dend + j < L);
+		p.home = true;
+		if (p.pend) {
+			const int koff = 2 * (rev ? dv.dstart - j : dv.dstart + j);
+			const u32 *w = wbase + (koff >> 5);
+			const int r = koff & 31;
+			const u32 w0 = w[0], w1 = w[1], w2 = w[2];
+			const u32 klo = __funnelshift_r(w0, w1, r) & kmlo, khi = __funnelshift_r(w1, w2, r) & kmhi;
+			p.key = ((u64)khi << 32) | klo;
+			p.h = slot_hash(p.key) & dv.slot_mask & ~1u;
+			p.s0 = __ldg(&dv.slots[p.h]);
+			p.s1 = __ldg(&dv.slots[p.h + 1]);
+			c_probes++;
+		}
+	};
+
+	// L2 prefetch of the bucket that the probe for shift j will read (used one round ahead in a fruitless search)
+	auto prefetch = [&](int j) {
+		if (dict_on && j < a.maxmatch && (rev ? dv.dstart > j : dv.dend + j < L)) {
+			const int koff = 2 * (rev ? dv.dstart - j : dv.dstart + j);
+			const u32 *w = wbase + (koff >> 5);
+			const int r = koff & 31;
+			const u32 w0 = w[0], w1 = w[1], w2 = w[2];
+			const u32 klo = __funnelshift_r(w0, w1, r) & kmlo, khi = __funnelshift_r(w1, w2, r) & kmhi;
+			const u32 h = slot_hash(((u64)khi << 32) | klo) & dv.slot_mask & ~1u;
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(&dv.slots[h]));
+		}
+	};
+	Probe pc;
+	pc.pend = false;
+
+	while (state != S_DONE) {
 		PROF_T0();
-
 		// ---- new chain head (reorder.cpp:650-688).  The reference takes the highest unclaimed index through a private
 		// downward cursor per thread.  Here the reads are cut into one stripe per walker; a walker scans its own stripe
 		// downward first and then the following stripes, so concurrent restarts do not fight over one bit.  With one
 		// walker the stripe is the whole array and the choice is exactly the reference's.
-		if (__any_sync(FULL, state == S_RESTART)) {
-			if (state == S_RESTART) {
-				bool got_head = false;
-				u32 stripe = s.stripe, tried = s.stripes_tried;
-				long long cursor = s.cursor;
-				while (tried < a.walkers) {
-					const long long slo = (long long)(((u64)stripe * a.n_loc) / a.walkers);
-					if (cursor < slo) {
-						// stripe exhausted: everything in it is claimed for good
-						if (leader) a.stripe_done[stripe] = 1u;
-						// move to the next stripe (cyclically) that is not known to be finished, G flags at a time
-						bool found_stripe = false;
-						while (tried + 1 < a.walkers) {
-							const u32 span = min((u32)G, a.walkers - 1 - tried);
-							u32 cs = stripe + 1 + sub;
-							if (cs >= a.walkers) cs -= a.walkers;
-							const bool open_ = (u32)sub < span && ldvol(&a.stripe_done[cs]) == 0u;
-							const u32 bal = __ballot_sync(gmask, open_) >> gbase;
-							if (bal) {
-								const u32 f = __ffs(bal) - 1;
-								stripe = stripe + 1 + f;
-								if (stripe >= a.walkers) stripe -= a.walkers;
-								tried += f + 1;
-								found_stripe = true;
-								break;
-							}
-							stripe += span;
+		if (state == S_RESTART) {
+			bool got_head = false;
+			u32 stripe = s.stripe, tried = s.stripes_tried;
+			long long cursor = s.cursor;
+			while (tried < a.walkers) {
+				const long long slo = (long long)(((u64)stripe * a.n_loc) / a.walkers);
+				if (cursor < slo) {
+					// stripe exhausted: everything in it is claimed for good
+					if (leader) a.stripe_done[stripe] = 1u;
+					// move to the next stripe (cyclically) that is not known to be finished, 32 flags at a time
+					bool found_stripe = false;
+					while (tried + 1 < a.walkers) {
+						const u32 span = min(32u, a.walkers - 1 - tried);
+						u32 cs = stripe + 1 + lane;
+						if (cs >= a.walkers) cs -= a.walkers;
+						const bool open_ = (u32)lane < span && ldvol(&a.stripe_done[cs]) == 0u;
+						const u32 bal = __ballot_sync(FULL, open_);
+						if (bal) {
+							const u32 f = __ffs(bal) - 1;
+							stripe = stripe + 1 + f;
 							if (stripe >= a.walkers) stripe -= a.walkers;
-							tried += span;
+							tried += f + 1;
+							found_stripe = true;
+							break;
 						}
-						if (!found_stripe) { tried = a.walkers; break; }
-						cursor = (long long)((((u64)stripe + 1) * a.n_loc) / a.walkers) - 1;
-						continue;
+						stripe += span;
+						if (stripe >= a.walkers) stripe -= a.walkers;
+						tried += span;
 					}
-					const long long topw = cursor >> 5;
-					const long long wi = topw - sub;
-					u32 word = (wi >= 0 && wi >= (slo >> 5)) ? ldvol(&a.claim[wi]) : 0u;
-					if (sub == 0) { int bt = (int)(cursor & 31); if (bt != 31) word &= (2u << bt) - 1u; }
-					if (wi == (slo >> 5)) word &= ~((1u << (slo & 31)) - 1u);
-					const u32 bal = __ballot_sync(gmask, word != 0u) >> gbase;
-					if (!bal) { cursor = (topw - (G - 1)) * 32 - 1; continue; }
-					const int src = __ffs(bal) - 1;
-					const u32 wv = __shfl_sync(gmask, word, gbase + src);
-					const int bit = 31 - __clz(wv);
-					const u32 j = (u32)((topw - src) * 32 + bit);
-					int got = leader ? (int)try_claim(a, a.base + j) : 0;
-					got = __shfl_sync(gmask, got, gbase);
-					cursor = (long long)j - 1; // j is claimed now, by this walker or by another one
-					if (got) { current = a.base + j; got_head = true; break; }
+					if (!found_stripe) { tried = a.walkers; break; }
+					cursor = (long long)((((u64)stripe + 1) * a.n_loc) / a.walkers) - 1;
+					continue;
 				}
-				if (leader) { s.stripe = stripe; s.stripes_tried = tried; s.cursor = cursor; }
-				if (got_head) { state = S_NEWHEAD; c_restart += leader; }
-				else {
-					state = S_DONE;
-					if (leader && s.chunk != NONE) a.chunk_fill[s.chunk] = s.fill;
-				}
+				const long long topw = cursor >> 5;
+				const long long wi = topw - lane;
+				u32 word = (wi >= 0 && wi >= (slo >> 5)) ? ldvol(&a.claim[wi]) : 0u;
+				if (lane == 0) { int bt = (int)(cursor & 31); if (bt != 31) word &= (2u << bt) - 1u; }
+				if (wi == (slo >> 5)) word &= ~((1u << (slo & 31)) - 1u);
+				const u32 bal = __ballot_sync(FULL, word != 0u);
+				if (!bal) { cursor = (topw - 31) * 32 - 1; continue; }
+				const int src = __ffs(bal) - 1;
+				const u32 wv = __shfl_sync(FULL, word, src);
+				const int bit = 31 - __clz(wv);
+				const u32 j = (u32)((topw - src) * 32 + bit);
+				int got = leader ? (int)try_claim(a, a.base + j) : 0;
+				got = __shfl_sync(FULL, got, 0);
+				cursor = (long long)j - 1; // j is claimed now, by this walker or by another one
+				if (got) { current = a.base + j; got_head = true; break; }
+			}
+			if (leader) { s.stripe = stripe; s.stripes_tried = tried; s.cursor = cursor; }
+			if (got_head) { state = S_NEWHEAD; c_restart += leader; }
+			else {
+				state = S_DONE;
+				if (leader && s.chunk != NONE) a.chunk_fill[s.chunk] = s.fill;
+				break;
 			}
 		}
-
 		PROF_ADD(0);
-		// ---- start a chain at `current`: the window is the read itself (reorder.cpp:875-883); with the left extension the
-		// walk starts on the reverse-complement strand
-		if (__any_sync(FULL, state == S_NEWHEAD)) {
-			if (state == S_NEWHEAD) {
-				__syncwarp(gmask);
-				if (sub < NW) s.cur[sub] = __ldg(&a.reads[(size_t)current * NW + sub]);
-				__syncwarp(gmask);
-				left_mode = a.extend != 0;
-				update_ref<NW, G>(s, L, sub, gmask, true, left_mode, 0, head);
-				prev = current;
-				prev_unmatched = true;
-				jb = 0;
-				state = S_SEARCH;
-			}
-		}
 
+		// ---- start a chain at `current`: the window is the read itself (reorder.cpp:875-883); with the left extension the
+		// walk starts on the reverse-complement strand.  A walker whose last heads all stayed alone (the tail of the job,
+		// where the unclaimed reads are the ones no dictionary window finds) goes right only.
+		if (state == S_NEWHEAD) {
+			__syncwarp();
+			if (lane < W2) s.cur[lane] = __ldg(reinterpret_cast<const u32 *>(a.reads + (size_t)current * NW) + lane);
+			__syncwarp();
+			left_mode = a.extend != 0 && dry < DRY_HEADS;
+			update_ref<NW>(s, L, lane, true, left_mode, 0, head);
+			prev = current;
+			prev_unmatched = true;
+			jb = 0;
+			state = S_SEARCH;
+		}
 		PROF_ADD(1);
-		// ---- search round: the four probe kinds of SPR * U consecutive shifts.  Every lane first issues its U slot loads
-		// (independent, so their latencies overlap), then the hits are worked off in shift order.
-		const bool searching = state == S_SEARCH;
+
+		// ---- search round: the four probe kinds of SPR consecutive shifts from jb on, one probe per lane.  After a round
+		// without a match the buckets of the following round are prefetched into L2 while this round is worked off.
 		bool found = false;
 		u32 k_rid = 0;
 		int k_j = 0, k_rev = 0;
-		{
-			const int jq = sub >> 2;
-			const int ucur = G == 32 ? (jb == 0 ? 1 : 2) : U; // warp-uniform
-			u32 blo[UX], bsize[UX];
-			{
-				u64 keys[UX];
-				u32 hs[UX];
-				ulonglong2 sl0[UX], sl1[UX];
-#pragma unroll
-				for (int u = 0; u < UX; u++) {
-					const int j = jb + u * SPR + jq;
-					const bool valid = u < ucur && searching && dict_on && j < a.maxmatch && (rev ? dv.dstart > j : dv.dend + j < L);
-					keys[u] = 0; hs[u] = 0; sl0[u] = sl1[u] = make_ulonglong2(0ull, 0ull);
-					if (valid) {
-						keys[u] = rev ? getbits(s.rref, NW, 2 * (dv.dstart - j), kb) : getbits(s.ref, NW, 2 * (dv.dstart + j), kb);
-						hs[u] = slot_hash(keys[u]) & dv.slot_mask & ~1u;
-						sl0[u] = __ldg(&dv.slots[hs[u]]);
-						sl1[u] = __ldg(&dv.slots[hs[u] + 1]);
+		if (state == S_SEARCH) {
+			const int j = jb + jq;
+			issue(j, pc);
+			if (jb > 0) prefetch(j + SPR);
+			c_steps += leader && jb == 0;
+			PROF_CNT(8, 1);
+			PROF_CNT(9, jb == 0);
+
+			// The lanes are worked off in lane order = the sequential order of the reference.  A lane is PENDING while its
+			// bucket chain is not resolved, then owns a BIN whose entries it tests from the tail (reorder.cpp:540), and is a
+			// CAND once an entry passed the Hamming test.  The lowest CAND may claim as soon as no PENDING lane precedes it;
+			// lanes behind it are never waited for.
+			int ps = pc.pend ? P_PENDING : P_DEAD;
+			u32 lo = 0, size = 0, left = 0, cand = NONE;
+			int seen = 0;
+			u32 rw[W2];
+			const int off = rev ? -2 * j : 2 * j;
+			const u32 *hw = wbase + (off >> 5);
+			const int hr = off & 31;
+			const u32 *hm = mbase + j * W2;
+			while (true) {
+				if (ps == P_PENDING) {
+					const int r = bucket_step(pc.key, pc.s0, pc.s1, pc.home, lo, size);
+					if (r == 1) { ps = P_BIN; left = size; c_hits++; }
+					else if (r == 0) ps = P_DEAD;
+					else {
+						pc.home = false;
+						pc.h = (pc.h + 2) & dv.slot_mask;
+						pc.s0 = __ldg(&dv.slots[pc.h]);
+						pc.s1 = __ldg(&dv.slots[pc.h + 1]);
 					}
-					c_probes += valid;
 				}
-#pragma unroll
-				for (int u = 0; u < UX; u++) { // finish the lookups (rarely more than the one bucket already loaded)
-					blo[u] = 0; bsize[u] = 0;
-					dict_resolve(dv, keys[u], hs[u], sl0[u], sl1[u], blo[u], bsize[u]);
-					c_hits += bsize[u] != 0u;
-				}
-			}
-			c_steps += leader && searching && jb == 0;
-			PROF_ADD(2);
-			PROF_CNT(8, searching);
-			PROF_CNT(9, searching && jb == 0);
-#pragma unroll
-			for (int u = 0; u < UX; u++) {
-				if (!__any_sync(FULL, bsize[u] != 0u && !found)) continue;
-				const int j = jb + u * SPR + jq;
-				const u32 lo = blo[u], size = bsize[u];
-				// candidate scan: entries of the bin not looked at yet (from the tail, reorder.cpp:540), live entries seen so far
-				u32 left = found ? 0u : size;
-				int seen = 0;
-				u32 cand = NONE;
-				u64 rw[NW];
-				auto advance = [&]() {
-					cand = NONE;
+				if (ps == P_BIN) {
+					ps = P_DEAD;
 					while (left > 0 && seen < a.maxsearch) {
 						left--;
 						const u32 rid = bin_entry(dv, lo, size, left);
@@ -459,46 +493,39 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 						if (!((cw >> (rid & 31)) & 1u)) continue; // removed from the bin in the reference (505-514)
 						seen++;
 						c_cmp++;
-						if (hamming<NW>(s, rw, L, j, rev) <= a.thresh) { cand = rid; break; }
+						if (hamming<NW>(hw, hr, hm, rw) <= a.thresh) { cand = rid; ps = P_CAND; break; }
 					}
-				};
-				if (left) advance();
-				while (true) {
-					const u32 ball = __ballot_sync(FULL, cand != NONE);
-					if (!ball) break;
-					const u32 bal = (ball & gmask) >> gbase;
-					if (bal) {
-						const int win = __ffs(bal) - 1;
-						int got = 0;
-						if (sub == win) {
-							got = try_claim(a, cand);
-							if (!got) c_fail++;
-						}
-						got = __shfl_sync(gmask, got, gbase + win);
-						if (got) {
-							found = true;
-							k_rid = __shfl_sync(gmask, cand, gbase + win);
-							k_j = jb + u * SPR + (win >> 2);
-							k_rev = (win & 3) >= 2;
-							if (sub == win) {
+				}
+				const u32 bc = __ballot_sync(FULL, ps == P_CAND), bp = __ballot_sync(FULL, ps == P_PENDING);
+				if (!(bc | bp)) break; // nothing matches in these shifts
+				if (bc && (!bp || (bc & (0u - bc)) < (bp & (0u - bp)))) {
+					const int win = __ffs(bc) - 1;
+					int got = 0;
+					if (lane == win) {
+						got = try_claim(a, cand);
+						if (!got) { c_fail++; ps = P_BIN; }
+					}
+					got = __shfl_sync(FULL, got, win);
+					if (got) {
+						found = true;
+						k_rid = __shfl_sync(FULL, cand, win);
+						k_j = jb + (win >> 2);
+						k_rev = (win & 3) >= 2;
+						if (lane == win) {
 #pragma unroll
-								for (int k = 0; k < NW; k++) s.cur[k] = rw[k];
-							}
-							cand = NONE;
-						} else if (sub == win) advance();
+							for (int k = 0; k < W2; k++) s.cur[k] = rw[k];
+						}
+						break;
 					}
 				}
 			}
-		}
+			PROF_ADD(2);
 
-		PROF_ADD(3);
-		PROF_CNT(10, found);
-		// ---- a read was appended (reorder.cpp:560-578 / 624-641)
-		if (__any_sync(FULL, found)) {
 			if (found) {
+				// ---- a read was appended (reorder.cpp:560-578 / 624-641)
 				current = k_rid;
-				__syncwarp(gmask);
-				update_ref<NW, G>(s, L, sub, gmask, false, k_rev != 0, k_j, head);
+				__syncwarp();
+				update_ref<NW>(s, L, lane, false, k_rev != 0, k_j, head);
 				if (leader) {
 					if (!left_mode) {
 						if (prev_unmatched) emit(mkrec(prev, (u32)L, 0, 0, 0));
@@ -514,56 +541,58 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, (NW <= 4 ? 8 : 4) / (G == 8 ?
 					}
 				}
 				if (!left_mode) prev_unmatched = false;
+				dry = 0;
 				jb = 0;
+					PROF_CNT(10, 1);
+			} else {
+				jb += SPR;
+				if (jb >= a.maxmatch) state = S_CHAINEND;
 			}
-		}
-		if (searching && !found) {
-			jb += SPR * (G == 32 ? (jb == 0 ? 1 : 2) : U);
-			if (jb >= a.maxmatch) state = S_CHAINEND;
+			PROF_ADD(4);
 		}
 
-		PROF_ADD(4);
 		// ---- nothing matches the window any more
-		if (__any_sync(FULL, state == S_CHAINEND)) {
-			if (state == S_CHAINEND) {
-				if (left_mode) {
-					// the left run ends: write it in front of the head, last found first, then walk right from the head
-					__syncwarp(gmask);
-					const u32 k = s.lcount;
-					if (k > 0) {
-						if (leader) lemit(mkrec(s.pend, (u32)L, s.pend_f ^ 1u, 0, 0)); // leftmost read = head of the chain
-						__syncwarp(gmask);
-						u32 c = s.lchunk, f = s.lfill, remaining = k;
-						while (remaining) {
-							const u32 take = min(min(f, (u32)G), remaining);
-							u64 r = 0;
-							if ((u32)sub < take) r = __ldcg(&a.lrecs[(size_t)c * CHUNK + f - 1 - sub]);
-							for (u32 t = 0; t < take; t++) {
-								const u64 rr = __shfl_sync(gmask, r, gbase + t);
-								if (leader) emit(rr);
-							}
-							f -= take;
-							remaining -= take;
-							if (f == 0 && remaining) { c = __ldcg(&a.lprev[c]); f = CHUNK; }
+		if (state == S_CHAINEND) {
+			if (left_mode) {
+				// the left run ends: write it in front of the head, last found first, then walk right from the head
+				__syncwarp();
+				const u32 k = s.lcount;
+				if (k > 0) {
+					if (leader) lemit(mkrec(s.pend, (u32)L, s.pend_f ^ 1u, 0, 0)); // leftmost read = head of the chain
+					__syncwarp();
+					u32 c = s.lchunk, f = s.lfill, remaining = k;
+					while (remaining) {
+						const u32 take = min(min(f, 32u), remaining);
+						u64 r = 0;
+						if ((u32)lane < take) r = __ldcg(&a.lrecs[(size_t)c * CHUNK + f - 1 - lane]);
+						for (u32 t = 0; t < take; t++) {
+							const u64 rr = __shfl_sync(FULL, r, t);
+							if (leader) emit(rr);
 						}
-						if (leader) {
-							emit(mkrec(prev, s.j1, 0, 1, 0));
-							s.lchunk = s.lfirst; s.lfill = 0; s.lcount = 0; // keep one chunk for the next left run
-						}
-						prev_unmatched = false;
+						f -= take;
+						remaining -= take;
+						if (f == 0 && remaining) { c = __ldcg(&a.lprev[c]); f = CHUNK; }
 					}
-					left_mode = false;
-					current = prev;
-					__syncwarp(gmask);
-					if (sub < NW) s.cur[sub] = __ldg(&a.reads[(size_t)current * NW + sub]);
-					__syncwarp(gmask);
-					update_ref<NW, G>(s, L, sub, gmask, true, false, 0, head);
-					jb = 0;
-					state = S_SEARCH;
-				} else {
-					if (leader && prev_unmatched) emit(mkrec(prev, 0, 0, 0, 1)); // the head stayed alone: singleton (672-684)
-					state = S_RESTART;
+					if (leader) {
+						emit(mkrec(prev, s.j1, 0, 1, 0));
+						s.lchunk = s.lfirst; s.lfill = 0; s.lcount = 0; // keep one chunk for the next left run
+					}
+					prev_unmatched = false;
 				}
+				left_mode = false;
+				current = prev;
+				__syncwarp();
+				if (lane < W2) s.cur[lane] = __ldg(reinterpret_cast<const u32 *>(a.reads + (size_t)current * NW) + lane);
+				__syncwarp();
+				update_ref<NW>(s, L, lane, true, false, 0, head);
+				jb = 0;
+				state = S_SEARCH;
+			} else {
+				if (prev_unmatched) {
+					if (leader) emit(mkrec(prev, 0, 0, 0, 1)); // the head stayed alone: singleton (672-684)
+					dry++;
+				}
+				state = S_RESTART;
 			}
 		}
 		PROF_ADD(5);
@@ -645,59 +674,46 @@ __global__ void __launch_bounds__(256) chunk_gather_kernel(const u64 *__restrict
 	}
 }
 
-template <int NW, int G>
+template <int NW>
+size_t walk_smem(const WalkArgs &a)
+{
+	return sizeof(WalkerSmem<NW>) * WALK_WARPS + (size_t)2 * a.maxmatch * 2 * NW * sizeof(u32);
+}
+template <int NW>
 int launch_walk(harcgpu_ctx *c, const WalkArgs &a)
 {
-	constexpr int WPB = WALK_WARPS * 32 / G; // walkers per block
-	size_t smem = sizeof(WalkerSmem<NW>) * WPB;
-	CK(cudaFuncSetAttribute(walk_kernel<NW, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	walk_kernel<NW, G><<<KL + cdiv(a.walkers, WPB), WALK_WARPS * 32, smem, c->st>>>(a);
+	const size_t smem = walk_smem<NW>(a);
+	CK(cudaFuncSetAttribute(walk_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	walk_kernel<NW><<<KL + cdiv(a.walkers, WALK_WARPS), WALK_WARPS * 32, smem, c->st>>>(a);
 	CK(cudaGetLastError());
 	return 0;
 }
 
 // walkers that can be resident at once: a walker that is not resident only starts after the others have finished
-template <int NW, int G>
-int resident_walkers(harcgpu_ctx *c, u32 *out)
+template <int NW>
+int resident_walkers(harcgpu_ctx *c, const WalkArgs &a, u32 *out)
 {
-	constexpr int WPB = WALK_WARPS * 32 / G;
-	size_t smem = sizeof(WalkerSmem<NW>) * WPB;
+	const size_t smem = walk_smem<NW>(a);
 	int nb = 0, sms = 0;
-	CK(cudaFuncSetAttribute(walk_kernel<NW, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, walk_kernel<NW, G>, WALK_WARPS * 32, smem));
+	CK(cudaFuncSetAttribute(walk_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, walk_kernel<NW>, WALK_WARPS * 32, smem));
 	CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-	*out = (u32)nb * (u32)sms * WPB;
+	*out = (u32)nb * (u32)sms * WALK_WARPS;
 	return 0;
 }
 } // namespace
 
-#define DISPATCH_NW_G(NWv, Gv, CALL)                                                                \
-	switch ((NWv) * 100 + (Gv)) {                                                                   \
-	case 108: { constexpr int NW = 1, G = 8; CALL; } break;                                          \
-	case 208: { constexpr int NW = 2, G = 8; CALL; } break;                                          \
-	case 308: { constexpr int NW = 3, G = 8; CALL; } break;                                          \
-	case 408: { constexpr int NW = 4, G = 8; CALL; } break;                                          \
-	case 508: { constexpr int NW = 5, G = 8; CALL; } break;                                          \
-	case 608: { constexpr int NW = 6, G = 8; CALL; } break;                                          \
-	case 708: { constexpr int NW = 7, G = 8; CALL; } break;                                          \
-	case 808: { constexpr int NW = 8, G = 8; CALL; } break;                                          \
-	case 116: { constexpr int NW = 1, G = 16; CALL; } break;                                         \
-	case 216: { constexpr int NW = 2, G = 16; CALL; } break;                                         \
-	case 316: { constexpr int NW = 3, G = 16; CALL; } break;                                         \
-	case 416: { constexpr int NW = 4, G = 16; CALL; } break;                                         \
-	case 516: { constexpr int NW = 5, G = 16; CALL; } break;                                         \
-	case 616: { constexpr int NW = 6, G = 16; CALL; } break;                                         \
-	case 716: { constexpr int NW = 7, G = 16; CALL; } break;                                         \
-	case 816: { constexpr int NW = 8, G = 16; CALL; } break;                                         \
-	case 132: { constexpr int NW = 1, G = 32; CALL; } break;                                         \
-	case 232: { constexpr int NW = 2, G = 32; CALL; } break;                                         \
-	case 332: { constexpr int NW = 3, G = 32; CALL; } break;                                         \
-	case 432: { constexpr int NW = 4, G = 32; CALL; } break;                                         \
-	case 532: { constexpr int NW = 5, G = 32; CALL; } break;                                         \
-	case 632: { constexpr int NW = 6, G = 32; CALL; } break;                                         \
-	case 732: { constexpr int NW = 7, G = 32; CALL; } break;                                         \
-	case 832: { constexpr int NW = 8, G = 32; CALL; } break;                                         \
-	default: harcgpu_set_error("unsupported read length %d / lanes per walker %d", c->L, (int)(Gv)); return -1; \
+#define DISPATCH_NW(NWv, CALL)                                                              \
+	switch (NWv) {                                                                          \
+	case 1: { constexpr int NW = 1; CALL; } break;                                          \
+	case 2: { constexpr int NW = 2; CALL; } break;                                          \
+	case 3: { constexpr int NW = 3; CALL; } break;                                          \
+	case 4: { constexpr int NW = 4; CALL; } break;                                          \
+	case 5: { constexpr int NW = 5; CALL; } break;                                          \
+	case 6: { constexpr int NW = 6; CALL; } break;                                          \
+	case 7: { constexpr int NW = 7; CALL; } break;                                          \
+	case 8: { constexpr int NW = 8; CALL; } break;                                          \
+	default: harcgpu_set_error("unsupported read length %d", c->L); return -1;              \
 	}
 
 int s1_init_claim(harcgpu_ctx *c, u32 *claim, u32 n)
@@ -726,11 +742,11 @@ int s1_reorder(harcgpu_ctx *c)
 	// heads), capped at what is resident at once.
 	u32 resident = 0;
 	int rc = -1;
-	int lanes = c->p.lanes_per_walker;
-	if (const char *e = getenv("HARCGPU_LANES")) lanes = atoi(e); // tuning aid
-	if (lanes == 0) lanes = 32;
-	if (lanes != 8 && lanes != 16 && lanes != 32) { harcgpu_set_error("lanes_per_walker must be 8, 16 or 32"); return -1; }
-	DISPATCH_NW_G(c->NW, lanes, (rc = resident_walkers<NW, G>(c, &resident)));
+	if (c->p.lanes_per_walker != 0 && c->p.lanes_per_walker != 32) { harcgpu_set_error("lanes_per_walker: a walker is one warp (0 or 32)"); return -1; }
+	if (c->p.maxmatch < 1 || c->p.maxmatch > 16 * c->NW) { harcgpu_set_error("maxmatch %d out of range for read length %d", c->p.maxmatch, c->L); return -1; }
+	WalkArgs a;
+	a.maxmatch = c->p.maxmatch;
+	DISPATCH_NW(c->NW, (rc = resident_walkers<NW>(c, a, &resident)));
 	if (rc) return rc;
 	// one job on several GPUs: this GPU's walkers own the id range [base, base + n_loc) for starts and restarts
 	const bool sharded = c->shard_world > 1;
@@ -767,7 +783,6 @@ int s1_reorder(harcgpu_ctx *c)
 	if (c->alloc(&stripe_done, walkers)) return -1;
 	CK(cudaMemsetAsync(stripe_done, 0, 4 * (size_t)walkers, st));
 
-	WalkArgs a;
 	a.reads = c->reads; a.n = n; a.L = c->L; a.maxmatch = c->p.maxmatch; a.thresh = c->p.thresh; a.maxsearch = c->p.maxsearch;
 	a.numdict = c->p.numdict; a.extend = extend;
 	for (int l = 0; l < 2; l++) {
@@ -783,7 +798,7 @@ int s1_reorder(harcgpu_ctx *c)
 	a.lrecs = lrecs; a.lprev = lprev; a.lchunk_ctr = ctrs + 1; a.max_lchunks = max_chunks;
 	a.counters = c->counters;
 	c->tic();
-	DISPATCH_NW_G(c->NW, lanes, (rc = launch_walk<NW, G>(c, a)));
+	DISPATCH_NW(c->NW, (rc = launch_walk<NW>(c, a)));
 	if (rc) return rc;
 	c->toc("walk");
 	CK(cudaGetLastError());
@@ -793,7 +808,7 @@ int s1_reorder(harcgpu_ctx *c)
 		CK(cudaStreamSynchronize(st));
 		CK(cudaMemcpyFromSymbol(h, g_walk_prof, sizeof h));
 		CK(cudaMemcpyToSymbol(g_walk_prof, z, sizeof z));
-		fprintf(stderr, "WALK_PROF walkers %u cycles: restart %llu newhead %llu probe %llu cand %llu append %llu chainend %llu | rounds %llu steps %llu found %llu | warp life avg %llu max %llu warps %llu\n",
+		fprintf(stderr, "WALK_PROF walkers %u cycles: restart %llu newhead %llu search %llu (unused %llu) append %llu chainend %llu | rounds %llu steps %llu found %llu | warp life avg %llu max %llu warps %llu\n",
 		        walkers, h[0], h[1], h[2], h[3], h[4], h[5], h[8], h[9], h[10], h[13] ? h[11] / h[13] : 0ull, h[12], h[13]);
 	}
 #endif
