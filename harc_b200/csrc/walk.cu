@@ -159,8 +159,10 @@ __device__ __forceinline__ void update_ref(WalkerSmem<NW> &s, int L, int lane, b
 		v.z += cc == 2u ? 4u : 0u;
 		v.w += cc == 3u ? 4u : 0u;
 		u32 b = max(max(v.x, v.y), max(v.z, v.w));
-		if (i < L) s.key[idx] = v;
-		else b = 3u; // beyond the read: base A, the zero bits of the reference's bitset
+		// positions beyond the read (i >= L) live in slots that no valid position uses (LP >= L) and that are re-initialised
+		// when they enter the window, so the store needs no guard; their base is A, the zero bits of the reference's bitset
+		s.key[idx] = v;
+		if (i >= L) b = 3u;
 		out |= ((0x27u >> (2 * (b & 3u))) & 3u) << (2 * t); // tie rank 3,2,1,0 -> code A0 C2 G1 T3
 		if (++r == B) { r = 0; q++; }
 	}
@@ -246,8 +248,9 @@ struct Probe {
 	bool pend, home;
 };
 
-template <int NW>
-__global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? 8 : 4) walk_kernel(WalkArgs a)
+// MB = blocks per SM the register allocation is bounded for (8 -> 64 registers, 10 -> 48, 12 -> 40)
+template <int NW, int MB>
+__global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
 {
 	constexpr int W2 = 2 * NW;
 	extern __shared__ uint4 smem_raw[];
@@ -325,25 +328,35 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? 8 : 4) walk_kernel(
 	const int jq = lane >> 2;
 	const bool rev = kind >= 2;
 	const int l = kind & 1;
-	const bool dict_on = l < a.numdict;
 	const DictView dv = a.d[l];
+	const bool full64 = a.kbits[0] == 64 && a.kbits[a.numdict - 1] == 64; // warp-uniform: keys need no masking
 	const int kb = a.kbits[l];
-	const u32 kmlo = lowmask32(kb), kmhi = lowmask32(kb - 32);
+	const int step2 = rev ? -2 : 2;       // a shift by one base moves this lane's windows by step2 bits
 	const u32 *wbase = rev ? s.rref : s.ref;
 	const u32 *mbase = mtab + (rev ? a.maxmatch * W2 : 0);
+	// bit r of vmask: this lane's probe exists in the round that starts at shift 8r (reorder.cpp:520-523, 585-588)
+	u32 vmask = 0;
+	for (int r = 0; SPR * r < a.maxmatch; r++) {
+		const int j = SPR * r + jq;
+		if (l < a.numdict && j < a.maxmatch && (rev ? dv.dstart > j : dv.dend + j < L)) vmask |= 1u << r;
+	}
 
 	// issue the probe of this lane for shift j: key = the dictionary window of the consensus moved by j
+	auto probe_key = [&](int j, u64 &key, u32 &h) {
+		const int koff = 2 * dv.dstart + step2 * j;
+		const u32 *w = wbase + (koff >> 5);
+		const int r = koff & 31;
+		const u32 w0 = w[0], w1 = w[1], w2 = w[2];
+		u32 klo = __funnelshift_r(w0, w1, r), khi = __funnelshift_r(w1, w2, r);
+		if (!full64) { klo &= lowmask32(kb); khi &= lowmask32(kb - 32); }
+		key = ((u64)khi << 32) | klo;
+		h = slot_hash(key) & dv.slot_mask & ~1u;
+	};
 	auto issue = [&](int j, Probe &p) {
-		p.pend = dict_on && j < a.maxmatch && (rev ? dv.dstart > j : dv.dend + j < L);
+		p.pend = (vmask >> (j >> 3)) & 1u;
 		p.home = true;
 		if (p.pend) {
-			const int koff = 2 * (rev ? dv.dstart - j : dv.dstart + j);
-			const u32 *w = wbase + (koff >> 5);
-			const int r = koff & 31;
-			const u32 w0 = w[0], w1 = w[1], w2 = w[2];
-			const u32 klo = __funnelshift_r(w0, w1, r) & kmlo, khi = __funnelshift_r(w1, w2, r) & kmhi;
-			p.key = ((u64)khi << 32) | klo;
-			p.h = slot_hash(p.key) & dv.slot_mask & ~1u;
+			probe_key(j, p.key, p.h);
 			p.s0 = __ldg(&dv.slots[p.h]);
 			p.s1 = __ldg(&dv.slots[p.h + 1]);
 			c_probes++;
@@ -352,13 +365,10 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? 8 : 4) walk_kernel(
 
 	// L2 prefetch of the bucket that the probe for shift j will read (used one round ahead in a fruitless search)
 	auto prefetch = [&](int j) {
-		if (dict_on && j < a.maxmatch && (rev ? dv.dstart > j : dv.dend + j < L)) {
-			const int koff = 2 * (rev ? dv.dstart - j : dv.dstart + j);
-			const u32 *w = wbase + (koff >> 5);
-			const int r = koff & 31;
-			const u32 w0 = w[0], w1 = w[1], w2 = w[2];
-			const u32 klo = __funnelshift_r(w0, w1, r) & kmlo, khi = __funnelshift_r(w1, w2, r) & kmhi;
-			const u32 h = slot_hash(((u64)khi << 32) | klo) & dv.slot_mask & ~1u;
+		if ((vmask >> (j >> 3)) & 1u) {
+			u64 key;
+			u32 h;
+			probe_key(j, key, h);
 			asm volatile("prefetch.global.L2 [%0];" ::"l"(&dv.slots[h]));
 		}
 	};
@@ -467,7 +477,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? 8 : 4) walk_kernel(
 			u32 lo = 0, size = 0, left = 0, cand = NONE;
 			int seen = 0;
 			u32 rw[W2];
-			const int off = rev ? -2 * j : 2 * j;
+			const int off = step2 * j;
 			const u32 *hw = wbase + (off >> 5);
 			const int hr = off & 31;
 			const u32 *hm = mbase + j * W2;
@@ -679,41 +689,50 @@ size_t walk_smem(const WalkArgs &a)
 {
 	return sizeof(WalkerSmem<NW>) * WALK_WARPS + (size_t)2 * a.maxmatch * 2 * NW * sizeof(u32);
 }
-template <int NW>
+template <int NW, int MB>
 int launch_walk(harcgpu_ctx *c, const WalkArgs &a)
 {
 	const size_t smem = walk_smem<NW>(a);
-	CK(cudaFuncSetAttribute(walk_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	walk_kernel<NW><<<KL + cdiv(a.walkers, WALK_WARPS), WALK_WARPS * 32, smem, c->st>>>(a);
+	CK(cudaFuncSetAttribute(walk_kernel<NW, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	walk_kernel<NW, MB><<<KL + cdiv(a.walkers, WALK_WARPS), WALK_WARPS * 32, smem, c->st>>>(a);
 	CK(cudaGetLastError());
 	return 0;
 }
 
 // walkers that can be resident at once: a walker that is not resident only starts after the others have finished
-template <int NW>
+template <int NW, int MB>
 int resident_walkers(harcgpu_ctx *c, const WalkArgs &a, u32 *out)
 {
 	const size_t smem = walk_smem<NW>(a);
 	int nb = 0, sms = 0;
-	CK(cudaFuncSetAttribute(walk_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, walk_kernel<NW>, WALK_WARPS * 32, smem));
+	CK(cudaFuncSetAttribute(walk_kernel<NW, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, walk_kernel<NW, MB>, WALK_WARPS * 32, smem));
 	CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
 	*out = (u32)nb * (u32)sms * WALK_WARPS;
 	return 0;
 }
 } // namespace
 
-#define DISPATCH_NW(NWv, CALL)                                                              \
-	switch (NWv) {                                                                          \
-	case 1: { constexpr int NW = 1; CALL; } break;                                          \
-	case 2: { constexpr int NW = 2; CALL; } break;                                          \
-	case 3: { constexpr int NW = 3; CALL; } break;                                          \
-	case 4: { constexpr int NW = 4; CALL; } break;                                          \
-	case 5: { constexpr int NW = 5; CALL; } break;                                          \
-	case 6: { constexpr int NW = 6; CALL; } break;                                          \
-	case 7: { constexpr int NW = 7; CALL; } break;                                          \
-	case 8: { constexpr int NW = 8; CALL; } break;                                          \
-	default: harcgpu_set_error("unsupported read length %d", c->L); return -1;              \
+// reads of up to 128 bases (NW <= 4) come in three register budgets, longer ones in one
+#define DISPATCH_NW(NWv, MBv, CALL)                                                         \
+	switch ((NWv) * 100 + ((NWv) <= 4 ? (MBv) : 4)) {                                       \
+	case 108: { constexpr int NW = 1, MB = 8; CALL; } break;                                \
+	case 208: { constexpr int NW = 2, MB = 8; CALL; } break;                                \
+	case 308: { constexpr int NW = 3, MB = 8; CALL; } break;                                \
+	case 408: { constexpr int NW = 4, MB = 8; CALL; } break;                                \
+	case 110: { constexpr int NW = 1, MB = 10; CALL; } break;                               \
+	case 210: { constexpr int NW = 2, MB = 10; CALL; } break;                               \
+	case 310: { constexpr int NW = 3, MB = 10; CALL; } break;                               \
+	case 410: { constexpr int NW = 4, MB = 10; CALL; } break;                               \
+	case 112: { constexpr int NW = 1, MB = 12; CALL; } break;                               \
+	case 212: { constexpr int NW = 2, MB = 12; CALL; } break;                               \
+	case 312: { constexpr int NW = 3, MB = 12; CALL; } break;                               \
+	case 412: { constexpr int NW = 4, MB = 12; CALL; } break;                               \
+	case 504: { constexpr int NW = 5, MB = 4; CALL; } break;                                \
+	case 604: { constexpr int NW = 6, MB = 4; CALL; } break;                                \
+	case 704: { constexpr int NW = 7, MB = 4; CALL; } break;                                \
+	case 804: { constexpr int NW = 8, MB = 4; CALL; } break;                                \
+	default: harcgpu_set_error("unsupported read length %d / walk variant %d", c->L, (int)(MBv)); return -1; \
 	}
 
 int s1_init_claim(harcgpu_ctx *c, u32 *claim, u32 n)
@@ -746,7 +765,9 @@ int s1_reorder(harcgpu_ctx *c)
 	if (c->p.maxmatch < 1 || c->p.maxmatch > 16 * c->NW) { harcgpu_set_error("maxmatch %d out of range for read length %d", c->p.maxmatch, c->L); return -1; }
 	WalkArgs a;
 	a.maxmatch = c->p.maxmatch;
-	DISPATCH_NW(c->NW, (rc = resident_walkers<NW>(c, a, &resident)));
+	int mb = 8;
+	if (const char *e = getenv("HARCGPU_WALK_MB")) mb = atoi(e); // tuning aid: 8, 10 or 12 blocks per SM
+	DISPATCH_NW(c->NW, mb, (rc = resident_walkers<NW, MB>(c, a, &resident)));
 	if (rc) return rc;
 	// one job on several GPUs: this GPU's walkers own the id range [base, base + n_loc) for starts and restarts
 	const bool sharded = c->shard_world > 1;
@@ -798,7 +819,7 @@ int s1_reorder(harcgpu_ctx *c)
 	a.lrecs = lrecs; a.lprev = lprev; a.lchunk_ctr = ctrs + 1; a.max_lchunks = max_chunks;
 	a.counters = c->counters;
 	c->tic();
-	DISPATCH_NW(c->NW, (rc = launch_walk<NW>(c, a)));
+	DISPATCH_NW(c->NW, mb, (rc = launch_walk<NW, MB>(c, a)));
 	if (rc) return rc;
 	c->toc("walk");
 	CK(cudaGetLastError());
