@@ -66,6 +66,8 @@ struct harcgpu_ctx {
 	u64 *poolN = nullptr;   // [n_s+n_N][NW] bit 2i set where base i is N; 3-bit code of encoder.cpp:731-745 = 2*code2 + nflag
 	u32 *pool_order = nullptr; // order_s (encoder.cpp:865-870)
 	DictDev d2[2];
+	u32 *bloom2 = nullptr;  // blocked Bloom filter over the keys of d2[0] and d2[1] (stage2.cu: bloom_pos)
+	u32 bloom2_mask = 0;
 	// ---- stage II outputs
 	bool encoded = false;
 	std::vector<SetOut> sets;

@@ -136,24 +136,61 @@ __global__ void __launch_bounds__(256) finish_layout_kernel(const u32 *__restric
 }
 
 // ---------------------------------------------------------------------------------------------- consensus
-// One lane per column, one warp per 32 columns = one u64 of the packed consensus (encoder.cpp:619-652).
-__global__ void __launch_bounds__(256) consensus_kernel(const u64 *__restrict__ G, const u64 *__restrict__ sreads, u32 m, int L, int NW,
-                                                        u64 TOT, u64 *__restrict__ cons2)
+// buildcontig (encoder.cpp:619-652).  A block owns CONS_T consecutive columns.  The stream reads that cover them are a
+// contiguous index range (G is non-decreasing); they are staged in shared memory in chunks (start column relative to
+// the tile + packed bases), and every warp then runs over the reads that touch its 32 columns with all lanes on the
+// same read: the start column is a broadcast, the packed words of a read are read by neighbouring lanes from the same
+// one or two words, and a lane adds the base that falls on its column to four 16-bit counters packed in one u64
+// (flushed to 32-bit counters after every chunk, so nothing can overflow).
+constexpr int CONS_T = 256;   // columns per block
+constexpr int CONS_R = 512;   // reads per staged chunk
+__global__ void __launch_bounds__(CONS_T) consensus_kernel(const u64 *__restrict__ G, const u32 *__restrict__ sreads32, u32 m, int L, int W2,
+                                                           u64 TOT, u64 *__restrict__ cons2)
 {
-	const u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const int lane = threadIdx.x & 31;
-	if (w * 32 >= TOT) return;
-	const u64 g = w * 32 + lane;
+	extern __shared__ u32 cons_smem[];
+	int *sG = reinterpret_cast<int *>(cons_smem);      // [CONS_R] start column - c0
+	u32 *sW = cons_smem + CONS_R;                      // [CONS_R][W2]
+	__shared__ u32 s_range[2];
+	const int tid = threadIdx.x, lane = tid & 31;
+	const u64 c0 = (u64)blockIdx.x * CONS_T;
+	if (tid == 0) {
+		const u64 last = min(c0 + CONS_T - 1, TOT - 1);
+		s_range[0] = c0 >= (u64)L ? upper_bound64(G, m, c0 - L) : 0u; // first read with G + L > c0
+		s_range[1] = upper_bound64(G, m, last);                        // first read that starts behind the tile
+	}
+	__syncthreads();
+	const u32 rlo = s_range[0], rhi = s_range[1];
+	const int wc0 = tid & ~31;                         // first column of this warp, relative to c0
+	u32 cA = 0, cG = 0, cC = 0, cT = 0;
+	for (u32 base = rlo; base < rhi; base += CONS_R) {
+		const u32 nch = min((u32)CONS_R, rhi - base);
+		for (u32 k = tid; k < nch; k += CONS_T) sG[k] = (int)(long long)(__ldg(&G[base + k]) - c0);
+		for (u32 k = tid; k < nch * (u32)W2; k += CONS_T) sW[k] = __ldg(&sreads32[(size_t)base * W2 + k]);
+		__syncthreads();
+		// reads of the chunk that touch this warp's columns: start in (wc0 - L, wc0 + 31]
+		u32 klo = 0, khi = nch;
+		{
+			u32 lo = 0, hi = nch;
+			while (lo < hi) { u32 mid = (lo + hi) >> 1; if (sG[mid] <= wc0 - L) lo = mid + 1; else hi = mid; }
+			klo = lo;
+			hi = nch;
+			while (lo < hi) { u32 mid = (lo + hi) >> 1; if (sG[mid] <= wc0 + 31) lo = mid + 1; else hi = mid; }
+			khi = lo;
+		}
+		u64 cnt = 0; // four 16-bit counters, bit-code order A G C T; a chunk adds at most CONS_R votes
+		for (u32 k = klo; k < khi; k++) {
+			const u32 o = (u32)(tid - sG[k]);
+			if (o < (u32)L) {
+				const u32 v = (sW[k * W2 + (o >> 4)] >> (2 * (o & 15))) & 3u;
+				cnt += 1ull << (16 * v);
+			}
+		}
+		cA += (u32)cnt & 0xffffu; cG += (u32)(cnt >> 16) & 0xffffu; cC += (u32)(cnt >> 32) & 0xffffu; cT += (u32)(cnt >> 48);
+		__syncthreads();
+	}
+	const u64 g = c0 + tid;
 	u32 code = 0;
 	if (g < TOT) {
-		u32 hi = upper_bound64(G, m, g);
-		u32 lo = g >= (u64)L ? upper_bound64(G, m, g - L) : 0u;
-		u32 cA = 0, cC = 0, cG = 0, cT = 0;
-		for (u32 i = lo; i < hi; i++) {
-			u32 o = (u32)(g - __ldg(&G[i]));
-			u32 v = (u32)(__ldg(&sreads[(size_t)i * NW + (o >> 5)]) >> (2 * (o & 31))) & 3u;
-			cA += v == 0; cG += v == 1; cC += v == 2; cT += v == 3;
-		}
 		// ties -> A < C < G < T, strict '>' from max = 0 (encoder.cpp:642-648)
 		u32 mx = 0;
 		if (cA > mx) { mx = cA; code = 0; }
@@ -162,7 +199,7 @@ __global__ void __launch_bounds__(256) consensus_kernel(const u64 *__restrict__ 
 		if (cT > mx) { mx = cT; code = 3; }
 	}
 	u32 b0 = __ballot_sync(0xffffffffu, code & 1u), b1 = __ballot_sync(0xffffffffu, (code >> 1) & 1u);
-	if (lane == 0) {
+	if (lane == 0 && (g < TOT)) {
 		u64 lo = b0, hi = b1, v = 0;
 		// interleave
 		lo = (lo | (lo << 16)) & 0x0000FFFF0000FFFFull; lo = (lo | (lo << 8)) & 0x00FF00FF00FF00FFull;
@@ -172,7 +209,7 @@ __global__ void __launch_bounds__(256) consensus_kernel(const u64 *__restrict__ 
 		hi = (hi | (hi << 4)) & 0x0F0F0F0F0F0F0F0Full; hi = (hi | (hi << 2)) & 0x3333333333333333ull;
 		hi = (hi | (hi << 1)) & 0x5555555555555555ull;
 		v = lo | (hi << 1);
-		cons2[w] = v;
+		cons2[g >> 5] = v;
 	}
 }
 
@@ -187,23 +224,72 @@ struct PoolArgs {
 	int L, thresh_s, maxsearch;
 	u64 *best;
 	u64 rank_bits; // rank << RANK_SHIFT
+	const u32 *bloom; u32 bloom_mask;
 };
 
-__device__ __forceinline__ u64 spread2to3(u64 k2, int nb) // base t: 2-bit code c -> 3-bit code 2c at bits 3t
+// base t: 2-bit code c -> 3-bit code 2c at bits 3t (nb <= 21 bases): the groups are moved apart in five doubling steps
+__device__ __forceinline__ u64 spread2to3(u64 k2, int nb)
 {
-	u64 k3 = 0;
-	for (int t = 0; t < nb; t++) k3 |= (((k2 >> (2 * t)) & 3ull) << 1) << (3 * t);
-	return k3;
+	u64 x = nb < 32 ? k2 & ((1ull << (2 * nb)) - 1) : k2;
+	// (masks generated and checked against the per-base loop for every nb <= 21)
+	x = (x & 0x00000000ffffffffull) | ((x & 0x000003ff00000000ull) << 16); // bases 16..20 move by 16
+	x = (x & 0x03ff00000000ffffull) | ((x & 0x00000000ffff0000ull) << 8);  // bases with bit 3 set move by 8
+	x = (x & 0x00ff0000ff0000ffull) | ((x & 0x030000ff0000ff00ull) << 4);  // bit 2: by 4
+	x = (x & 0x300f00f00f00f00full) | ((x & 0x00f00f00f00f00f0ull) << 2);  // bit 1: by 2
+	x = (x & 0x30c30c30c30c30c3ull) | ((x & 0x030c30c30c30c30cull) << 1);  // bit 0: by 1
+	return x << 1;
 }
 
-template <int NW>
-__global__ void __launch_bounds__(128) pool_probe_kernel(PoolArgs a)
+// Blocked Bloom filter over the keys of both pool dictionaries (one 32-bit word per key, two bits in it): most window
+// keys of the consensus are in neither dictionary, and the filter (a few MB, L2 resident) answers those without
+// touching the key tables in DRAM.
+__device__ __forceinline__ void bloom_pos(u64 key, int l, u32 mask, u32 &word, u32 &bits)
 {
-	const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	u64 h = (key ^ (l ? 0x9E3779B97F4A7C15ull : 0ull)) * 0xD6E8FEB86659FD93ull;
+	h ^= h >> 32;
+	word = (u32)(h >> 10) & mask;
+	bits = (1u << ((u32)h & 31u)) | (1u << (((u32)h >> 5) & 31u));
+}
+__global__ void __launch_bounds__(256) bloom_insert_kernel(const u64 *__restrict__ keys, u32 nk, int l, u32 *bloom, u32 mask)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nk) return;
+	u32 w, b;
+	bloom_pos(keys[i], l, mask, w, b);
+	atomicOr(&bloom[w], b);
+}
+
+constexpr int PROBE_T = 128;  // window starts per block
+constexpr int PROBE_R = 768;  // stream reads whose start columns are staged per block
+template <int NW>
+__global__ void __launch_bounds__(PROBE_T) pool_probe_kernel(PoolArgs a)
+{
+	__shared__ int sG[PROBE_R];
+	__shared__ u32 s_range[2];
+	const int tid = threadIdx.x;
+	const u64 g0 = (u64)blockIdx.x * PROBE_T, g = g0 + tid;
 	const int L = a.L;
-	if (a.TOT < (u64)L || g > a.TOT - L) return;
-	// which contig does column g belong to, and may a window start here?
-	u32 r = upper_bound64(a.G, a.m, g) - 1;
+	const u64 glast = a.TOT - L; // last window start; the launch guarantees TOT >= L
+	// which contig does column g belong to?  r = last read with G[r] <= g.  One search per block for both ends of the
+	// tile, then the start columns in between are staged and every thread searches those.
+	if (tid == 0) {
+		s_range[0] = upper_bound64(a.G, a.m, g0) - 1;
+		s_range[1] = upper_bound64(a.G, a.m, min(g0 + PROBE_T - 1, glast));
+	}
+	__syncthreads();
+	const u32 r0 = s_range[0], r1 = s_range[1];
+	const bool staged = r1 - r0 <= (u32)PROBE_R;
+	if (staged) {
+		for (u32 k = tid; k < r1 - r0; k += PROBE_T) sG[k] = (int)(long long)(__ldg(&a.G[r0 + k]) - g0);
+		__syncthreads();
+	}
+	if (g > glast) return;
+	u32 r;
+	if (staged) {
+		u32 lo = 0, hi = r1 - r0;
+		while (lo < hi) { u32 mid = (lo + hi) >> 1; if (sG[mid] <= tid) lo = mid + 1; else hi = mid; }
+		r = r0 + lo - 1;
+	} else r = upper_bound64(a.G, a.m, g) - 1;
 	u32 c = __ldg(&a.cid[r]);
 	u32 next = c + 1 < a.NC ? __ldg(&a.cstart[c + 1]) : a.m;
 	if (next == a.m || next % a.per == 0) return; // last contig of its thread range: written without alignment (encoder.cpp:438-441)
@@ -221,8 +307,12 @@ __global__ void __launch_bounds__(128) pool_probe_kernel(PoolArgs a)
 			k2 = getbits_g(a.cons2, 2 * (g + L - 1 - dv.dend), 2 * nb);
 			k2 = revpairs64(~k2 & lowmask(2 * nb)) >> (64 - 2 * nb);
 		}
+		const u64 k3 = spread2to3(k2, nb);
+		u32 bw, bb;
+		bloom_pos(k3, l, a.bloom_mask, bw, bb);
+		if ((__ldg(&a.bloom[bw]) & bb) != bb) continue;
 		u32 bstart, bsize;
-		if (!dict_lookup(dv, spread2to3(k2, nb), bstart, bsize)) continue;
+		if (!dict_lookup(dv, k3, bstart, bsize)) continue;
 		if (!have_w) { load_window<NW>(a.cons2, g, L, w); have_w = true; }
 		if (rev && !have_rc) {
 			u64 t[NW];
@@ -537,6 +627,8 @@ static void free_pool(harcgpu_ctx *c)
 	c->release(c->pool); c->release(c->poolN); c->release(c->pool_order);
 	c->pool = c->poolN = nullptr; c->pool_order = nullptr;
 	for (int l = 0; l < 2; l++) free_dict(c, c->d2[l]);
+	c->release(c->bloom2);
+	c->bloom2 = nullptr;
 	c->pool_set = false; c->encoded = false;
 }
 
@@ -648,6 +740,20 @@ static int load_pool_impl(harcgpu_ctx *c, const char *s_ascii, const u32 *order_
 	c->tic();
 	for (int l = 0; l < 2; l++)
 		if (build_dict(c, c->d2[l], c->pool, c->poolN, P, c->NW, ds[l], de[l], 3)) return -1;
+	{
+		// Bloom filter over both dictionaries: >= 16 bits per key
+		const u64 nk = (u64)c->d2[0].numkeys + c->d2[1].numkeys;
+		u64 words = 1024;
+		while (words * 32 < 16 * nk) words <<= 1;
+		c->release(c->bloom2);
+		c->bloom2 = nullptr;
+		if (c->alloc(&c->bloom2, words)) return -1;
+		c->bloom2_mask = (u32)(words - 1);
+		CK(cudaMemsetAsync(c->bloom2, 0, words * 4, st));
+		for (int l = 0; l < 2; l++)
+			if (c->d2[l].numkeys) bloom_insert_kernel<<<KL + cdiv(c->d2[l].numkeys, 256), 256, 0, st>>>(c->d2[l].keys, c->d2[l].numkeys, l, c->bloom2, c->bloom2_mask);
+		CK(cudaGetLastError());
+	}
 	c->toc("pooldict");
 	c->pool_set = true;
 	return 0;
@@ -709,7 +815,8 @@ int s2_encode(harcgpu_ctx *c)
 	if (c->alloc(&cons2, cwords + 2)) return -1;
 	CK(cudaMemsetAsync(cons2 + cwords, 0, 16, st));
 	if (m) {
-		consensus_kernel<<<KL + cdiv(cwords * 32, 256), 256, 0, st>>>(G, c->sreads, m, L, NWv, TOT, cons2);
+		const size_t csm = (size_t)CONS_R * (1 + 2 * NWv) * sizeof(u32);
+		consensus_kernel<<<KL + cdiv(TOT, CONS_T), CONS_T, csm, st>>>(G, reinterpret_cast<const u32 *>(c->sreads), m, L, 2 * NWv, TOT, cons2);
 		CK(cudaGetLastError());
 	}
 
@@ -732,8 +839,9 @@ int s2_encode(harcgpu_ctx *c)
 		}
 		a.L = L; a.thresh_s = c->p.thresh_s; a.maxsearch = c->p.maxsearch; a.best = best;
 		a.rank_bits = (u64)(c->shard_world > 1 ? c->shard_rank : 0) << RANK_SHIFT;
+		a.bloom = c->bloom2; a.bloom_mask = c->bloom2_mask;
 		u64 nwin = TOT - L + 1;
-		DISPATCH_NW(NWv, (pool_probe_kernel<NW><<<KL + cdiv(nwin, 128), 128, 0, st>>>(a)));
+		DISPATCH_NW(NWv, (pool_probe_kernel<NW><<<KL + cdiv(nwin, PROBE_T), PROBE_T, 0, st>>>(a)));
 		CK(cudaGetLastError());
 	}
 	if (P && c->shard_world > 1) {
