@@ -135,6 +135,22 @@ __global__ void __launch_bounds__(256) finish_layout_kernel(const u32 *__restric
 	if (cs[i]) cstart[c] = i;
 }
 
+// T[k] = first stream read that starts at column >= TILE_C * k: lets a block find the reads around its columns with two
+// loads instead of two 25-step binary searches by one thread
+constexpr int TILE_C = 128;
+__global__ void __launch_bounds__(256) tile_index_kernel(const u64 *__restrict__ G, u32 m, u32 nt, u32 *__restrict__ T)
+{
+	u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= nt) return;
+	const u64 v = (u64)TILE_C * k;
+	u64 lo = 0, hi = m;
+	while (lo < hi) {
+		u64 mid = (lo + hi) >> 1;
+		if (__ldg(&G[mid]) < v) lo = mid + 1; else hi = mid;
+	}
+	T[k] = (u32)lo;
+}
+
 // ---------------------------------------------------------------------------------------------- consensus
 // buildcontig (encoder.cpp:619-652).  A block owns CONS_T consecutive columns.  The stream reads that cover them are a
 // contiguous index range (G is non-decreasing); they are staged in shared memory in chunks (start column relative to
@@ -144,22 +160,18 @@ __global__ void __launch_bounds__(256) finish_layout_kernel(const u32 *__restric
 // (flushed to 32-bit counters after every chunk, so nothing can overflow).
 constexpr int CONS_T = 256;   // columns per block
 constexpr int CONS_R = 512;   // reads per staged chunk
-__global__ void __launch_bounds__(CONS_T) consensus_kernel(const u64 *__restrict__ G, const u32 *__restrict__ sreads32, u32 m, int L, int W2,
-                                                           u64 TOT, u64 *__restrict__ cons2)
+__global__ void __launch_bounds__(CONS_T) consensus_kernel(const u64 *__restrict__ G, const u32 *__restrict__ T, const u32 *__restrict__ sreads32,
+                                                           u32 m, int L, int W2, u64 TOT, u64 *__restrict__ cons2)
 {
 	extern __shared__ u32 cons_smem[];
 	int *sG = reinterpret_cast<int *>(cons_smem);      // [CONS_R] start column - c0
 	u32 *sW = cons_smem + CONS_R;                      // [CONS_R][W2]
-	__shared__ u32 s_range[2];
 	const int tid = threadIdx.x, lane = tid & 31;
 	const u64 c0 = (u64)blockIdx.x * CONS_T;
-	if (tid == 0) {
-		const u64 last = min(c0 + CONS_T - 1, TOT - 1);
-		s_range[0] = c0 >= (u64)L ? upper_bound64(G, m, c0 - L) : 0u; // first read with G + L > c0
-		s_range[1] = upper_bound64(G, m, last);                        // first read that starts behind the tile
-	}
-	__syncthreads();
-	const u32 rlo = s_range[0], rhi = s_range[1];
+	// reads that may cover the tile: from the first read of the TILE_C-column cell that holds column c0 - L + 1 (a few
+	// more than needed) to the first read that starts behind the tile
+	const u32 rlo = c0 >= (u64)L ? __ldg(&T[(c0 - L + 1) / TILE_C]) : 0u;
+	const u32 rhi = __ldg(&T[(c0 + CONS_T) / TILE_C]);
 	const int wc0 = tid & ~31;                         // first column of this warp, relative to c0
 	u32 cA = 0, cG = 0, cC = 0, cT = 0;
 	for (u32 base = rlo; base < rhi; base += CONS_R) {
@@ -225,6 +237,7 @@ struct PoolArgs {
 	u64 *best;
 	u64 rank_bits; // rank << RANK_SHIFT
 	const u32 *bloom; u32 bloom_mask;
+	const u32 *T; // tile index (TILE_C == PROBE_T)
 };
 
 // base t: 2-bit code c -> 3-bit code 2c at bits 3t (nb <= 21 bases): the groups are moved apart in five doubling steps
@@ -259,25 +272,20 @@ __global__ void __launch_bounds__(256) bloom_insert_kernel(const u64 *__restrict
 	atomicOr(&bloom[w], b);
 }
 
-constexpr int PROBE_T = 128;  // window starts per block
+constexpr int PROBE_T = TILE_C; // window starts per block
 constexpr int PROBE_R = 768;  // stream reads whose start columns are staged per block
 template <int NW>
 __global__ void __launch_bounds__(PROBE_T) pool_probe_kernel(PoolArgs a)
 {
 	__shared__ int sG[PROBE_R];
-	__shared__ u32 s_range[2];
 	const int tid = threadIdx.x;
 	const u64 g0 = (u64)blockIdx.x * PROBE_T, g = g0 + tid;
 	const int L = a.L;
 	const u64 glast = a.TOT - L; // last window start; the launch guarantees TOT >= L
-	// which contig does column g belong to?  r = last read with G[r] <= g.  One search per block for both ends of the
-	// tile, then the start columns in between are staged and every thread searches those.
-	if (tid == 0) {
-		s_range[0] = upper_bound64(a.G, a.m, g0) - 1;
-		s_range[1] = upper_bound64(a.G, a.m, min(g0 + PROBE_T - 1, glast));
-	}
-	__syncthreads();
-	const u32 r0 = s_range[0], r1 = s_range[1];
+	// which contig does column g belong to?  r = last read with G[r] <= g.  The start columns of the reads around the
+	// tile (from the last read before it to the first one behind it, via the tile index) are staged and searched.
+	const u32 t0 = __ldg(&a.T[blockIdx.x]);
+	const u32 r0 = t0 ? t0 - 1 : 0u, r1 = __ldg(&a.T[blockIdx.x + 1]);
 	const bool staged = r1 - r0 <= (u32)PROBE_R;
 	if (staged) {
 		for (u32 k = tid; k < r1 - r0; k += PROBE_T) sG[k] = (int)(long long)(__ldg(&a.G[r0 + k]) - g0);
@@ -786,6 +794,7 @@ int s2_encode(harcgpu_ctx *c)
 	const u32 per = m ? 1 + (m - 1) / K : 1; // encoder.cpp:171
 	u32 *ns = nullptr, *ex = nullptr, *nat_idx = nullptr, *cs = nullptr, *cid = nullptr, *cstart = nullptr, *d_tot32 = nullptr;
 	u64 *inc = nullptr, *G = nullptr, *scan_tmp = nullptr, *d_tot64 = nullptr, *cons2 = nullptr;
+	u32 *tile_idx = nullptr;
 	u32 NC = 0;
 	u64 TOT = 0;
 	size_t scan_n = std::max<size_t>(std::max<size_t>(m, P), 1);
@@ -815,8 +824,12 @@ int s2_encode(harcgpu_ctx *c)
 	if (c->alloc(&cons2, cwords + 2)) return -1;
 	CK(cudaMemsetAsync(cons2 + cwords, 0, 16, st));
 	if (m) {
+		// tile index: entries 0 .. TOT/TILE_C + CONS_T/TILE_C (the consensus tiles look one tile past their end)
+		const u32 nt = (u32)(TOT / TILE_C + CONS_T / TILE_C + 2);
+		if (c->alloc(&tile_idx, nt)) return -1;
+		tile_index_kernel<<<KL + cdiv(nt, 256), 256, 0, st>>>(G, m, nt, tile_idx);
 		const size_t csm = (size_t)CONS_R * (1 + 2 * NWv) * sizeof(u32);
-		consensus_kernel<<<KL + cdiv(TOT, CONS_T), CONS_T, csm, st>>>(G, reinterpret_cast<const u32 *>(c->sreads), m, L, 2 * NWv, TOT, cons2);
+		consensus_kernel<<<KL + cdiv(TOT, CONS_T), CONS_T, csm, st>>>(G, tile_idx, reinterpret_cast<const u32 *>(c->sreads), m, L, 2 * NWv, TOT, cons2);
 		CK(cudaGetLastError());
 	}
 
@@ -839,7 +852,7 @@ int s2_encode(harcgpu_ctx *c)
 		}
 		a.L = L; a.thresh_s = c->p.thresh_s; a.maxsearch = c->p.maxsearch; a.best = best;
 		a.rank_bits = (u64)(c->shard_world > 1 ? c->shard_rank : 0) << RANK_SHIFT;
-		a.bloom = c->bloom2; a.bloom_mask = c->bloom2_mask;
+		a.bloom = c->bloom2; a.bloom_mask = c->bloom2_mask; a.T = tile_idx;
 		u64 nwin = TOT - L + 1;
 		DISPATCH_NW(NWv, (pool_probe_kernel<NW><<<KL + cdiv(nwin, PROBE_T), PROBE_T, 0, st>>>(a)));
 		CK(cudaGetLastError());
@@ -1016,7 +1029,7 @@ int s2_encode(harcgpu_ctx *c)
 		c->esz.aligned_N = M - M_single;
 	}
 	c->s2_keep.push_back(posb); c->s2_keep.push_back(noise); c->s2_keep.push_back(noisepos);
-	void *tmp[] = { ns, ex, nat_idx, cs, cid, cstart, inc, G, scan_tmp, d_tot32, d_tot64, cons2, best, prio_u, iprio, af, exa, rid_u, irid,
+	void *tmp[] = { tile_idx, ns, ex, nat_idx, cs, cid, cstart, inc, G, scan_tmp, d_tot32, d_tot64, cons2, best, prio_u, iprio, af, exa, rid_u, irid,
 	                f_src, f_kind, f_col, nm1, noff, revc, isN, exN, ordv, uf, exU, ulist, d_tail };
 	for (void *q : tmp) c->release(q);
 	c->encoded = true;
