@@ -21,6 +21,7 @@ EXPORTS = [
     "harcgpu_load_pool_device", "harcgpu_launch_count", "harcgpu_stage_nreads",
     "harcgpu_shard_init", "harcgpu_shard_connect", "harcgpu_shard_reset", "harcgpu_set_pool_exchange", "harcgpu_load_pool_ids",
     "harcgpu_get_packed_order",
+    "harcgpu_fastq_readlen", "harcgpu_ingest_fastq", "harcgpu_ingest_fastq_device", "harcgpu_get_ingest", "harcgpu_load_pool_ingested",
 ]
 
 
@@ -42,6 +43,10 @@ class SetSizes(ctypes.Structure):
     _fields_ = [("seq_bytes", ctypes.c_uint64), ("seq_tail", ctypes.c_uint64), ("pos_bytes", ctypes.c_uint64),
                 ("noise_bytes", ctypes.c_uint64), ("noisepos_bytes", ctypes.c_uint64), ("rev_bytes", ctypes.c_uint64),
                 ("rev_tail", ctypes.c_uint64)]
+
+
+class IngestInfo(ctypes.Structure):
+    _fields_ = [("readlen", ctypes.c_uint32), ("total_reads", ctypes.c_uint64), ("n_clean", ctypes.c_uint32), ("n_N", ctypes.c_uint32)]
 
 
 class Counters(ctypes.Structure):
@@ -92,6 +97,11 @@ def load_library():
     lib.harcgpu_load_pool_ids.argtypes = [vp, vp, u32, vp, u32]
     lib.harcgpu_get_packed_order.argtypes = [vp, vp, vp, vp, vp]
     lib.harcgpu_launch_count.restype = ctypes.c_uint64
+    lib.harcgpu_fastq_readlen.argtypes = [vp, ctypes.c_uint64]
+    lib.harcgpu_ingest_fastq.argtypes = [vp, vp, ctypes.c_uint64, ctypes.POINTER(IngestInfo)]
+    lib.harcgpu_ingest_fastq_device.argtypes = [vp, vp, ctypes.c_uint64, ctypes.POINTER(IngestInfo)]
+    lib.harcgpu_get_ingest.argtypes = [vp, vp, vp, vp]
+    lib.harcgpu_load_pool_ingested.argtypes = [vp]
     lib.harcgpu_get_encode_sizes.argtypes = [vp, ctypes.POINTER(EncodeSizes)]
     lib.harcgpu_get_set_sizes.argtypes = [vp, ctypes.c_int, ctypes.POINTER(SetSizes)]
     lib.harcgpu_get_set.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
@@ -100,6 +110,12 @@ def load_library():
     lib.harcgpu_encode_dir.argtypes = [vp, cp]
     _lib = lib
     return lib
+
+
+def fastq_readlen(fastq):
+    """harc:44: length of the second line."""
+    a = np.frombuffer(fastq, dtype=np.uint8) if isinstance(fastq, (bytes, bytearray)) else fastq
+    return int(load_library().harcgpu_fastq_readlen(_ptr(a) if a.size else None, a.size))
 
 
 def launch_count():
@@ -160,6 +176,34 @@ class HarcGpu:
             self.close()
         except Exception:
             pass
+
+    # ---- fused ingest (preprocess.cpp)
+    def ingest_fastq(self, fastq):
+        """fastq: bytes / uint8 array with the whole FASTQ file.  Returns the harcgpu_ingest_info fields as a dict."""
+        a = np.frombuffer(fastq, dtype=np.uint8) if isinstance(fastq, (bytes, bytearray)) else fastq
+        self._keep = a
+        info = IngestInfo()
+        self._ck(self.lib.harcgpu_ingest_fastq(self.h, _ptr(a) if a.size else None, a.size, ctypes.byref(info)))
+        self._ingest = {k: int(getattr(info, k)) for k, _ in IngestInfo._fields_}
+        return dict(self._ingest)
+
+    def ingest_fastq_device(self, dptr, nbytes):
+        info = IngestInfo()
+        self._ck(self.lib.harcgpu_ingest_fastq_device(self.h, ctypes.c_void_p(dptr), nbytes, ctypes.byref(info)))
+        self._ingest = {k: int(getattr(info, k)) for k, _ in IngestInfo._fields_}
+        return dict(self._ingest)
+
+    def get_ingest(self):
+        """(input_clean.dna, input_N.dna, read_order_N.bin) as preprocess.cpp would have written them."""
+        i = self._ingest
+        clean = np.empty(i["n_clean"] * (self.L + 1), dtype=np.uint8)
+        dnaN = np.empty(i["n_N"] * (self.L + 1), dtype=np.uint8)
+        orderN = np.empty(i["n_N"], dtype=np.uint32)
+        self._ck(self.lib.harcgpu_get_ingest(self.h, _ptr(clean), _ptr(dnaN), _ptr(orderN)))
+        return clean, dnaN, orderN
+
+    def load_pool_ingested(self):
+        self._ck(self.lib.harcgpu_load_pool_ingested(self.h))
 
     # ---- stage I
     def load_reads(self, ascii_lines, n=None):

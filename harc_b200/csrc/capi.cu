@@ -144,6 +144,73 @@ int harcgpu_load_reads(harcgpu_ctx *c, const char *ascii, u32 n)
 	return rc;
 }
 
+// ---- fused ingest: preprocess.cpp:49-138 + reorder.cpp:240-263 ------------------------------------------------
+int harcgpu_fastq_readlen(const char *fastq, uint64_t nbytes)
+{
+	// harc:44  readlen=$(head -2 $filename | tail -1 | wc -L)
+	if (!fastq) return -1;
+	const char *end = fastq + nbytes;
+	const char *l1 = (const char *)memchr(fastq, '\n', nbytes);
+	if (!l1) return -1;
+	l1++;
+	const char *l2 = (const char *)memchr(l1, '\n', (size_t)(end - l1));
+	return (int)((l2 ? l2 : end) - l1);
+}
+
+int harcgpu_ingest_fastq_device(harcgpu_ctx *c, const void *d_fastq, uint64_t nbytes, harcgpu_ingest_info *info)
+{
+	if (!c || (!d_fastq && nbytes)) { harcgpu_set_error("null argument"); return -1; }
+	CK(cudaSetDevice(c->device));
+	for (int l = 0; l < 2; l++) free_dict(c, c->d1[l]);
+	c->dicts_built = false; c->reordered = false;
+	u64 total = 0;
+	u32 nc = 0, nn = 0;
+	if (ing_ingest(c, (const char *)d_fastq, nbytes, &total, &nc, &nn)) return -1;
+	if (info) { info->readlen = (uint32_t)c->L; info->total_reads = total; info->n_clean = nc; info->n_N = nn; }
+	return 0;
+}
+
+int harcgpu_ingest_fastq(harcgpu_ctx *c, const char *fastq, uint64_t nbytes, harcgpu_ingest_info *info)
+{
+	if (!c || (!fastq && nbytes)) { harcgpu_set_error("null argument"); return -1; }
+	CK(cudaSetDevice(c->device));
+	char *d = nullptr;
+	if (c->alloc(&d, nbytes + 16)) return -1;
+	CK(cudaMemcpyAsync(d, fastq, nbytes, cudaMemcpyHostToDevice, c->st));
+	int rc = harcgpu_ingest_fastq_device(c, d, nbytes, info);
+	CK(cudaStreamSynchronize(c->st));
+	c->release(d);
+	return rc;
+}
+
+int harcgpu_get_ingest(harcgpu_ctx *c, char *input_clean, char *input_N, uint32_t *order_N)
+{
+	if (!c || !c->reads) { harcgpu_set_error("nothing ingested"); return -1; }
+	CK(cudaSetDevice(c->device));
+	const size_t line = (size_t)c->L + 1;
+	if (input_clean && c->n) {
+		char *d = nullptr;
+		if (c->alloc(&d, (size_t)c->n * line)) return -1;
+		if (ing_unpack_clean(c, d)) return -1;
+		CK(cudaMemcpyAsync(input_clean, d, (size_t)c->n * line, cudaMemcpyDeviceToHost, c->st));
+		CK(cudaStreamSynchronize(c->st));
+		c->release(d);
+	}
+	if (input_N && c->ing_nN) CK(cudaMemcpyAsync(input_N, c->ing_N, (size_t)c->ing_nN * line, cudaMemcpyDeviceToHost, c->st));
+	if (order_N && c->ing_nN) CK(cudaMemcpyAsync(order_N, c->ing_orderN, 4 * (size_t)c->ing_nN, cudaMemcpyDeviceToHost, c->st));
+	CK(cudaStreamSynchronize(c->st));
+	return 0;
+}
+
+int harcgpu_load_pool_ingested(harcgpu_ctx *c)
+{
+	if (!c) { harcgpu_set_error("null argument"); return -1; }
+	if (!c->reordered) { harcgpu_set_error("harcgpu_load_pool_ingested needs the singletons of harcgpu_reorder on this context"); return -1; }
+	if (c->ing_nN && !c->ing_N) { harcgpu_set_error("nothing ingested"); return -1; }
+	CK(cudaSetDevice(c->device));
+	return s2_load_pool_dev(c, c->ing_N, c->ing_nN);
+}
+
 int harcgpu_build_dicts(harcgpu_ctx *c)
 {
 	if (!c || !c->reads) { harcgpu_set_error("load reads first"); return -1; }

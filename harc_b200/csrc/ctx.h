@@ -42,6 +42,10 @@ struct harcgpu_ctx {
 	bool shard_ready = false;
 	int (*pool_exchange)(void *user, void *d_best, uint64_t count) = nullptr;
 	void *pool_exchange_user = nullptr;
+	// fused ingest (ingest.cu): reads with N as ASCII lines + their record numbers (input_N.dna, read_order_N.bin)
+	char *ing_N = nullptr;
+	u32 *ing_orderN = nullptr;
+	u32 ing_nN = 0;
 	// finalized stage I streams (device)
 	bool reordered = false;
 	u32 n_matched = 0, n_single = 0, n_unmatched = 0;
@@ -154,6 +158,9 @@ struct harcgpu_ctx {
 	}
 };
 
+// ingest.cu
+int ing_ingest(harcgpu_ctx *c, const char *d_fastq, u64 nbytes, u64 *total_reads, u32 *n_clean, u32 *n_N);
+int ing_unpack_clean(harcgpu_ctx *c, char *d_out);
 // walk.cu
 int s1_init_claim(harcgpu_ctx *c, u32 *claim, u32 n);
 // stage1.cu

@@ -529,6 +529,9 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
 					}
 				}
 			}
+#ifdef WALK_PROF
+			if (dry >= DRY_HEADS) { PROF_ADD(3); PROF_CNT(6, 1); } else
+#endif
 			PROF_ADD(2);
 
 			if (found) {
@@ -829,8 +832,8 @@ int s1_reorder(harcgpu_ctx *c)
 		CK(cudaStreamSynchronize(st));
 		CK(cudaMemcpyFromSymbol(h, g_walk_prof, sizeof h));
 		CK(cudaMemcpyToSymbol(g_walk_prof, z, sizeof z));
-		fprintf(stderr, "WALK_PROF walkers %u cycles: restart %llu newhead %llu search %llu (unused %llu) append %llu chainend %llu | rounds %llu steps %llu found %llu | warp life avg %llu max %llu warps %llu\n",
-		        walkers, h[0], h[1], h[2], h[3], h[4], h[5], h[8], h[9], h[10], h[13] ? h[11] / h[13] : 0ull, h[12], h[13]);
+		fprintf(stderr, "WALK_PROF walkers %u cycles: restart %llu newhead %llu search %llu (+ in singleton streaks %llu) append %llu chainend %llu | rounds %llu (%llu in streaks) steps %llu found %llu | warp life avg %llu max %llu warps %llu\n",
+		        walkers, h[0], h[1], h[2], h[3], h[4], h[5], h[8], h[6], h[9], h[10], h[13] ? h[11] / h[13] : 0ull, h[12], h[13]);
 	}
 #endif
 

@@ -77,6 +77,29 @@ const char *harcgpu_last_error(void);
 uint64_t harcgpu_launch_count(void);
 int harcgpu_device_count(void);
 
+/* ---- fused ingest (preprocess.cpp) --------------------------------------------------------- */
+typedef struct {
+	uint32_t readlen;      /* the context's read length (every sequence line was checked against it) */
+	uint64_t total_reads;  /* "Total number of reads" (preprocess.cpp:134): complete four-line records */
+	uint32_t n_clean;      /* numreads.bin: reads without N (preprocess.cpp:129-131) */
+	uint32_t n_N;          /* lines of input_N.dna = entries of read_order_N.bin */
+} harcgpu_ingest_info;
+/* harc:44: length of the second line of the file (host side); <0 if there is none. */
+int harcgpu_fastq_readlen(const char *fastq, uint64_t nbytes);
+/* preprocess.cpp:49-138 without the intermediate files, fused with reorder.cpp:240-263: the FASTQ bytes (host memory)
+ * are copied to the device, split into reads without / with N and the clean reads packed 2 bits/base in place, i.e. the
+ * context is afterwards in the state harcgpu_load_reads leaves it in.  A sequence line whose length differs from the
+ * context's readlen fails like preprocess.cpp:92-97.  Quality values and ids (-q) are not handled here. */
+int harcgpu_ingest_fastq(harcgpu_ctx *ctx, const char *fastq, uint64_t nbytes, harcgpu_ingest_info *info);
+/* Same, from a buffer already resident in device memory (16-byte aligned). */
+int harcgpu_ingest_fastq_device(harcgpu_ctx *ctx, const void *d_fastq, uint64_t nbytes, harcgpu_ingest_info *info);
+/* The three files preprocess would have written: input_clean.dna (n_clean lines), input_N.dna (n_N lines),
+ * read_order_N.bin (n_N entries).  Any pointer may be NULL. */
+int harcgpu_get_ingest(harcgpu_ctx *ctx, char *input_clean, char *input_N, uint32_t *order_N);
+/* encoder.cpp:823-872 with the singletons of harcgpu_reorder and the reads with N of harcgpu_ingest_fastq, both
+ * already on the device. */
+int harcgpu_load_pool_ingested(harcgpu_ctx *ctx);
+
 /* ---- stage I (reorder.cpp) ------------------------------------------------------------------------------ */
 /* reorder.cpp:240-263 readDnaFile + 203-209 stringtobitset.  ascii = contents of input_clean.dna: n lines of
  * readlen chars in {A,C,G,T} + '\n' (host memory).  Copies to the device and packs 2 bits/base. */

@@ -53,3 +53,11 @@ def test_product_does_not_link_the_oracle():
         for f in files:
             if f.endswith((".cu", ".cuh", ".h", ".cpp", ".py")):
                 assert "oracle" not in open(os.path.join(root, f)).read().lower().replace("# oracle", ""), f
+
+
+def test_fastq_readlen_is_the_second_line():
+    """harc:44 (host side, no GPU needed)."""
+    import harc_b200
+    assert harc_b200.fastq_readlen(b"@id\nACGTACGTAC\n+\nIIIIIIIIII\n") == 10
+    assert harc_b200.fastq_readlen(b"@id\nACGT") == 4
+    assert harc_b200.fastq_readlen(b"@id") == -1
