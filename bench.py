@@ -134,6 +134,37 @@ def cpu_baseline(args):
                       % (n, L, genome, t1, t2)}
 
 
+def time_ingest(torch, harc_b200, all_lines, n, device):
+    """FASTQ of n reads (fixed-width ids, constant qualities) resident in HBM -> packed clean reads + N reads."""
+    rec = 11 + (L + 1) + 2 + (L + 1)
+    fq = np.empty((n, rec), dtype=np.uint8)
+    num = np.arange(n, dtype=np.int64)
+    fq[:, 0] = ord("@")
+    for k in range(9):
+        fq[:, 9 - k] = (num // 10 ** k) % 10 + 48
+    fq[:, 10] = 10
+    fq[:, 11:11 + L + 1] = all_lines[: n * (L + 1)].reshape(n, L + 1)
+    fq[:, 11 + L + 1] = ord("+")
+    fq[:, 11 + L + 2] = 10
+    fq[:, 11 + L + 3: rec - 1] = ord("I")
+    fq[:, rec - 1] = 10
+    d = torch.empty(fq.size + 16, dtype=torch.uint8, device="cuda")
+    d[: fq.size].copy_(torch.from_numpy(fq.reshape(-1)))
+    ctx = harc_b200.HarcGpu(L, device=device)
+    for _ in range(2):
+        info = ctx.ingest_fastq_device(d.data_ptr(), fq.size)
+    ms = []
+    for _ in range(3):
+        info = ctx.ingest_fastq_device(d.data_ptr(), fq.size)
+        ms.append(ctx.last_ms("ingest"))
+    want_N = int((all_lines[: n * (L + 1)].reshape(n, L + 1) == ord("N")).any(axis=1).sum())
+    assert info["total_reads"] == n and info["n_N"] == want_N, (info, want_N)
+    ctx.close()
+    t = float(np.median(ms))
+    return {"what": "fused FASTQ ingest (preprocess.cpp + readDnaFile), FASTQ resident in HBM", "reads": n, "fastq_bytes": int(fq.size),
+            "ms": t, "Mreads_per_s": n / t / 1e3, "GB_per_s": fq.size / t / 1e6}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -154,6 +185,8 @@ def main():
                          "memory, all-gather of singleton ids, all-reduce(min) of pool claims)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer pass")
+    ap.add_argument("--ingest-reads", type=float, default=8e6,
+                    help="reads of the workload that are also laid out as a FASTQ file to time the fused ingest (0 = skip)")
     args = ap.parse_args()
     args.reads = int(args.reads)
     args.genome = int(args.genome)
@@ -191,6 +224,11 @@ def main():
     d_clean[: h_clean.numel()].copy_(h_clean)
     d_N[: h_N.numel()].copy_(h_N)
     torch.cuda.synchronize()
+    # auxiliary figure: the fused FASTQ ingest (SURVEY f-1) on the first --ingest-reads reads laid out as a FASTQ file
+    ingest = None
+    n_ing = min(int(args.ingest_reads), args.reads) if world == 1 else 0
+    if n_ing:
+        ingest = time_ingest(torch, harc_b200, w["all"], n_ing, local)
     del w["all"]
 
     ctx = harc_b200.HarcGpu(L, device=local, walkers=args.walkers, file_sets=args.file_sets,
@@ -339,7 +377,7 @@ def main():
         "stage1": {"matched": m, "singletons": s, "chain_heads": u, "probes_per_read": cnt["probes"] / max(1, cnt["steps"]),
                    "compares_per_read": cnt["compares"] / max(1, cnt["steps"]), "claim_fails": cnt["claim_fails"]},
         "stage2": {"aligned_singletons": es.aligned_singletons, "aligned_N": es.aligned_N},
-        "roofline": {"bound": "hbm", "kernel": "walk_kernel<4, 32> (one walker per warp)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "walk_kernel<4, 8> (one walker per warp)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,
                      "algorithmic_bytes_per_clean_read": balg, "model_probes_per_read": P,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
@@ -349,6 +387,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
+    if ingest:
+        out["ingest"] = ingest
     if not args.no_cpu_baseline and world == 1:
         try:
             out["cpu_baseline"] = cpu_baseline(args)
