@@ -83,38 +83,58 @@ __global__ void __launch_bounds__(256) seq_offset_kernel(const char *__restrict_
 	}
 }
 
-// err[0] = 1 + length found for the first record (lowest number) whose sequence line is not L long; err[1] = its number
+// err[0] = (record number << 20 | length found) of the first record (lowest number) whose sequence line is not L long.
+// A warp works on ING_RPW consecutive records at a time and issues the byte loads of all of them before it looks at
+// any (the kernel is otherwise bound by the latency of one short dependent chain per warp).
+constexpr int ING_RPW = 4;  // records per warp and round
+constexpr int ING_MAXT = 8; // 32-byte slices of a line: readlen + 1 <= 256
 __global__ void __launch_bounds__(256) classify_kernel(const char *__restrict__ buf, u64 nbytes, const u64 *__restrict__ seq_off, u64 nrec,
                                                        int L, u32 *__restrict__ isN, unsigned long long *__restrict__ err)
 {
-	const u64 r = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const u64 r0 = (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * ING_RPW;
 	const int lane = threadIdx.x & 31;
-	if (r >= nrec) return;
-	const u64 off = seq_off[r];
-	bool hasN = false;
-	int nlpos = 0x7fffffff; // first newline / end of file inside the first L + 1 bytes of the line
-	for (int i = lane; i <= L; i += 32) {
-		const u64 p = off + i;
-		const char ch = p < nbytes ? buf[p] : '\n';
-		if (ch == '\n') nlpos = min(nlpos, i);
-		else if (i < L && ch == 'N') hasN = true;
-	}
-	for (int o = 16; o > 0; o >>= 1) nlpos = min(nlpos, __shfl_xor_sync(0xffffffffu, nlpos, o));
-	// an 'N' behind a premature newline does not count, but that line is an error anyway
-	const u32 anyN = __ballot_sync(0xffffffffu, hasN);
-	if (lane == 0) {
-		isN[r] = anyN ? 1u : 0u;
-		if (nlpos != L) {
-			// line shorter than L (nlpos < L) or longer (no newline up to byte L): report like preprocess.cpp:92-97
-			unsigned long long len = 0;
-			if (nlpos < L) len = (unsigned long long)nlpos;
-			else { // measure the long line
-				u64 p = off + L;
-				while (p < nbytes && buf[p] != '\n') p++;
-				len = p - off;
+	if (r0 >= nrec) return;
+	const int T = (L + 1 + 31) / 32;
+	u64 off[ING_RPW];
+	unsigned char ch[ING_RPW][ING_MAXT];
+#pragma unroll
+	for (int k = 0; k < ING_RPW; k++) off[k] = r0 + k < nrec ? __ldg(&seq_off[r0 + k]) : nbytes;
+#pragma unroll
+	for (int k = 0; k < ING_RPW; k++)
+#pragma unroll
+		for (int t = 0; t < ING_MAXT; t++) {
+			const u64 p = off[k] + lane + 32 * t;
+			ch[k][t] = (t < T && p < nbytes) ? (unsigned char)__ldg(&buf[p]) : (unsigned char)'\n'; // the end of the file ends a line
+		}
+#pragma unroll
+	for (int k = 0; k < ING_RPW; k++) {
+		const u64 r = r0 + k;
+		if (r >= nrec) break;
+		bool hasN = false;
+		int nlpos = 0x7fffffff; // first newline / end of file inside the first L + 1 bytes of the line
+#pragma unroll
+		for (int t = 0; t < ING_MAXT; t++) {
+			const int i = lane + 32 * t;
+			if (t < T && i <= L) {
+				if (ch[k][t] == '\n') nlpos = min(nlpos, i);
+				else if (i < L && ch[k][t] == 'N') hasN = true;
 			}
-			const unsigned long long key = (r << 20) | (len & 0xfffffull); // smallest record number wins
-			atomicMin(&err[0], key);
+		}
+		for (int o = 16; o > 0; o >>= 1) nlpos = min(nlpos, __shfl_xor_sync(0xffffffffu, nlpos, o));
+		const u32 anyN = __ballot_sync(0xffffffffu, hasN);
+		if (lane == 0) {
+			isN[r] = anyN ? 1u : 0u;
+			if (nlpos != L) {
+				// line shorter than L (nlpos < L) or longer (no newline up to byte L): report like preprocess.cpp:92-97
+				unsigned long long len = 0;
+				if (nlpos < L) len = (unsigned long long)nlpos;
+				else { // measure the long line
+					u64 p = off[k] + L;
+					while (p < nbytes && buf[p] != '\n') p++;
+					len = p - off[k];
+				}
+				atomicMin(&err[0], (r << 20) | (len & 0xfffffull)); // smallest record number wins
+			}
 		}
 	}
 }
@@ -123,30 +143,57 @@ __global__ void __launch_bounds__(256) emit_kernel(const char *__restrict__ buf,
                                                    int NW, const u32 *__restrict__ isN, const u32 *__restrict__ exN, u64 *__restrict__ reads,
                                                    char *__restrict__ outN, u32 *__restrict__ orderN)
 {
-	const u64 r = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const u64 r0 = (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * ING_RPW;
 	const int lane = threadIdx.x & 31;
-	if (r >= nrec) return;
-	const u64 off = seq_off[r];
-	const u32 nb = exN[r]; // reads with N before this record
-	if (isN[r]) {
-		char *dst = outN + (size_t)nb * (L + 1);
-		for (int i = lane; i < L; i += 32) dst[i] = buf[off + i];
-		if (lane == 0) { dst[L] = '\n'; orderN[nb] = (u32)r; }
-	} else {
-		unsigned char *dst = reinterpret_cast<unsigned char *>(reads + (size_t)(r - nb) * NW);
-		for (int k = lane; k < 8 * NW; k += 32) { // output byte k = bases 4k .. 4k+3
-			u32 v = 0;
+	if (r0 >= nrec) return;
+	// lane k packs output bytes k and k + 32 of a read (bases 4k .. 4k+3): up to 8 input bytes per record
+	u64 off[ING_RPW];
+	u32 nb[ING_RPW], fl[ING_RPW];
+	unsigned char ch[ING_RPW][8];
 #pragma unroll
-			for (int t = 0; t < 4; t++) {
-				const int i = 4 * k + t;
-				if (i < L) {
-					const u32 ch = (unsigned char)buf[off + i];
-					// (ch >> 1) & 3 is A0 C1 T2 G3; the reference's code (reorder.cpp:188-195) is A0 G1 C2 T3
-					const u32 b0 = (ch >> 1) & 1u, b1 = (ch >> 2) & 1u;
-					v |= ((((b0 ^ b1) << 1) | b1)) << (2 * t);
+	for (int k = 0; k < ING_RPW; k++) {
+		const bool ok = r0 + k < nrec;
+		off[k] = ok ? __ldg(&seq_off[r0 + k]) : 0;
+		nb[k] = ok ? __ldg(&exN[r0 + k]) : 0u; // reads with N before this record
+		fl[k] = ok ? __ldg(&isN[r0 + k]) : 0u;
+	}
+#pragma unroll
+	for (int k = 0; k < ING_RPW; k++)
+#pragma unroll
+		for (int t = 0; t < 8; t++) {
+			const int i = 4 * (lane + 32 * (t >> 2)) + (t & 3);
+			ch[k][t] = (r0 + k < nrec && i < L) ? (unsigned char)__ldg(&buf[off[k] + i]) : (unsigned char)'A';
+		}
+#pragma unroll
+	for (int k = 0; k < ING_RPW; k++) {
+		const u64 r = r0 + k;
+		if (r >= nrec) break;
+		if (fl[k]) {
+			char *dst = outN + (size_t)nb[k] * (L + 1);
+#pragma unroll
+			for (int t = 0; t < 8; t++) {
+				const int i = 4 * (lane + 32 * (t >> 2)) + (t & 3);
+				if (i < L) dst[i] = (char)ch[k][t];
+			}
+			if (lane == 0) { dst[L] = '\n'; orderN[nb[k]] = (u32)r; }
+		} else {
+			unsigned char *dst = reinterpret_cast<unsigned char *>(reads + (size_t)(r - nb[k]) * NW);
+#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				const int kb = lane + 32 * h; // output byte
+				if (kb < 8 * NW) {
+					u32 v = 0;
+#pragma unroll
+					for (int t = 0; t < 4; t++) {
+						// (ch >> 1) & 3 is A0 C1 T2 G3; the reference's code (reorder.cpp:188-195) is A0 G1 C2 T3; bases
+						// behind the end of the read were loaded as 'A' = 0
+						const u32 c = ch[k][4 * h + t];
+						const u32 b0 = (c >> 1) & 1u, b1 = (c >> 2) & 1u;
+						v |= (((b0 ^ b1) << 1) | b1) << (2 * t);
+					}
+					dst[kb] = (unsigned char)v;
 				}
 			}
-			dst[k] = (unsigned char)v;
 		}
 	}
 }
@@ -203,7 +250,7 @@ int ing_ingest(harcgpu_ctx *c, const char *d_fastq, u64 nbytes, u64 *total_reads
 		if (c->alloc(&scan_tmp, scan_tmp_elems(nrec))) return -1;
 		CK(cudaMemsetAsync(err, 0xff, 8, st));
 		seq_offset_kernel<<<KL + (unsigned)ntiles, 256, 0, st>>>(d_fastq, nbytes, base, nrec, seq_off);
-		classify_kernel<<<KL + cdiv(nrec * 32, 256), 256, 0, st>>>(d_fastq, nbytes, seq_off, nrec, L, isN, err);
+		classify_kernel<<<KL + cdiv((nrec + ING_RPW - 1) / ING_RPW * 32, 256), 256, 0, st>>>(d_fastq, nbytes, seq_off, nrec, L, isN, err);
 		CK(cudaGetLastError());
 		if (exclusive_scan_u32(isN, exN, nrec, scan_tmp, d_tot32, st)) return -1;
 		unsigned long long herr = 0;
@@ -221,7 +268,7 @@ int ing_ingest(harcgpu_ctx *c, const char *d_fastq, u64 nbytes, u64 *total_reads
 	if (c->alloc(&c->ing_N, (size_t)nN * (L + 1) + 16) || c->alloc(&c->ing_orderN, nN)) return -1;
 	c->ing_nN = nN;
 	if (nrec) {
-		emit_kernel<<<KL + cdiv(nrec * 32, 256), 256, 0, st>>>(d_fastq, nbytes, seq_off, nrec, L, c->NW, isN, exN, c->reads, c->ing_N, c->ing_orderN);
+		emit_kernel<<<KL + cdiv((nrec + ING_RPW - 1) / ING_RPW * 32, 256), 256, 0, st>>>(d_fastq, nbytes, seq_off, nrec, L, c->NW, isN, exN, c->reads, c->ing_N, c->ing_orderN);
 		CK(cudaGetLastError());
 	}
 	c->toc("ingest");

@@ -23,7 +23,6 @@
 namespace {
 constexpr int WALK_WARPS = 4;         // warps (= walkers) per block
 constexpr int CHUNK = 32;             // records per log chunk
-constexpr int SPR = 8;                // shifts probed per round
 constexpr u32 NONE = 0xffffffffu;
 constexpr u32 FULL = 0xffffffffu;
 constexpr int DRY_HEADS = 4;          // left extension is skipped after this many heads in a row that stayed alone
@@ -123,16 +122,16 @@ __device__ __forceinline__ u32 revpairs32(u32 x) // reverse the order of the 16 
 }
 __device__ __forceinline__ u32 lowmask32(int n) { return n >= 32 ? ~0u : (n <= 0 ? 0u : ((1u << n) - 1u)); }
 
-// updaterefcount (reorder.cpp:863-915) for one walker, by the 32 lanes of its warp.
-// Lane `lane` owns the B = NW consecutive window positions [B*lane, B*lane+B).  The votes of a position are four keys
+// updaterefcount (reorder.cpp:863-915) for one walker, by the G lanes of its group.
+// Lane `lane` owns the B = 32*NW/G consecutive window positions [B*lane, B*lane+B).  The votes of a position are four keys
 // (count << 2 | tie rank), one per base code (bit-code order A, G, C, T), in one uint4: a read adds one vote per
 // position, and argmax with ties -> A < C < G < T (strict '>' from max = 0, reorder.cpp:893-899) is the tie rank in
 // the low bits of the largest key.  The window is circular (origin `head`) over LP = 32*NW slots so that a shift
-// moves no data; slot p lives at index (p % B) * 32 + p / B, which makes the lanes touch 32 consecutive uint4.
-template <int NW>
-__device__ __forceinline__ void update_ref(WalkerSmem<NW> &s, int L, int lane, bool reset, bool rev, int shift, int &head)
+// moves no data; slot p lives at index (p % B) * G + p / B, which makes the lanes touch G consecutive uint4.
+template <int NW, int G>
+__device__ __forceinline__ void update_ref(WalkerSmem<NW> &s, int L, int lane, u32 gmask, bool reset, bool rev, int shift, int &head)
 {
-	constexpr int B = NW, LP = 32 * NW, W2 = 2 * NW;
+	constexpr int B = 32 * NW / G, LP = 32 * NW, W2 = 2 * NW; // `lane` = lane inside the walker's group of G
 	if (reset) head = 0;
 	else { head += shift; if (head >= LP) head -= LP; }
 	// the 2B bits of the new read that fall on this lane's positions (reverse-complemented first if rev)
@@ -149,7 +148,7 @@ __device__ __forceinline__ void update_ref(WalkerSmem<NW> &s, int L, int lane, b
 #pragma unroll
 	for (int t = 0; t < B; t++) {
 		const int i = B * lane + t;
-		const int idx = r * 32 + ((lane + q) & 31);
+		const int idx = r * G + ((lane + q) & (G - 1));
 		const u32 cc = (mine >> (2 * t)) & 3u;
 		uint4 v = s.key[idx];
 		// a position that enters the window starts from the bare tie ranks of A, G, C, T (bit-code order): 3, 1, 2, 0
@@ -169,15 +168,20 @@ __device__ __forceinline__ void update_ref(WalkerSmem<NW> &s, int L, int lane, b
 	if ((2 * B) % 8 == 0) {
 		unsigned char *rb = reinterpret_cast<unsigned char *>(s.ref) + (2 * B / 8) * lane;
 		if (2 * B == 8) *rb = (unsigned char)out;
-		else *reinterpret_cast<unsigned short *>(rb) = (unsigned short)out; // 2 * B == 16
-		__syncwarp();
-	} else { // pieces that are not whole bytes (2B <= 14 bits here) are OR-ed into the zeroed words
+		else if (2 * B == 16) *reinterpret_cast<unsigned short *>(rb) = (unsigned short)out;
+		else if (2 * B == 32) *reinterpret_cast<u32 *>(rb) = out;
+		else {
+#pragma unroll
+			for (int k = 0; k < 2 * B / 8; k++) rb[k] = (unsigned char)(out >> (8 * k));
+		}
+		__syncwarp(gmask);
+	} else { // pieces that are not whole bytes (2B <= 28 bits here) are OR-ed into the zeroed words
 		if (lane < W2) s.ref[lane] = 0u;
-		__syncwarp();
+		__syncwarp(gmask);
 		const int o = 2 * B * lane, w = o >> 5, sh = o & 31;
 		atomicOr(&s.ref[w], out << sh);
 		if (sh + 2 * B > 32) atomicOr(&s.ref[w + 1], out >> (32 - sh));
-		__syncwarp();
+		__syncwarp(gmask);
 	}
 	if (lane < W2) {
 		// rref = (ref with its 32*NW base pairs in reverse order) >> (64*NW - 2L), valid bits complemented
@@ -187,7 +191,7 @@ __device__ __forceinline__ void update_ref(WalkerSmem<NW> &s, int L, int lane, b
 		const u32 t1 = i1 >= 0 ? revpairs32(s.ref[i1]) : 0u;
 		s.rref[lane] = __funnelshift_r(t0, t1, sr) ^ lowmask32(2 * L - 32 * lane);
 	}
-	__syncwarp();
+	__syncwarp(gmask);
 }
 
 // popcount(ref ^ (read & mask[j])) with ref >>= 2j (forward, reorder.cpp:543) or
@@ -248,26 +252,33 @@ struct Probe {
 	bool pend, home;
 };
 
-// MB = blocks per SM the register allocation is bounded for (8 -> 64 registers, 10 -> 48, 12 -> 40)
-template <int NW, int MB>
-__global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
+// G = lanes per walker: 32 (one walker per warp, 8 shifts per round) or 16 (two walkers per warp, 4 shifts per round;
+// the two walkers share every instruction of a round while they are in the same phase).  `sub` is the lane inside the
+// walker's group; every warp-level primitive below is restricted to the group (gmask).
+template <int NW, int G>
+__global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? 8 : 4) walk_kernel(WalkArgs a)
 {
 	constexpr int W2 = 2 * NW;
+	constexpr int WPW = 32 / G;          // walkers per warp
+	constexpr int SPR = G / 4;           // shifts probed per round
+	constexpr int SPR_LOG = G == 32 ? 3 : 2;
 	extern __shared__ uint4 smem_raw[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const bool leader = lane == 0;
-	const u32 wid = blockIdx.x * WALK_WARPS + warp;
-	WalkerSmem<NW> &s = reinterpret_cast<WalkerSmem<NW> *>(smem_raw)[warp];
+	const int sub = lane & (G - 1), gbase = lane & ~(G - 1);
+	const u32 gmask = G == 32 ? FULL : (0xffffu << gbase);
+	const bool leader = sub == 0;
+	const u32 wid = (blockIdx.x * WALK_WARPS + warp) * WPW + lane / G;
+	WalkerSmem<NW> &s = reinterpret_cast<WalkerSmem<NW> *>(smem_raw)[warp * WPW + lane / G];
 	// compare masks, one row of W2 words per (direction, shift): forward bits [0, 2(L-j)), reverse bits [2j, 2L)
-	u32 *mtab = reinterpret_cast<u32 *>(smem_raw) + WALK_WARPS * (sizeof(WalkerSmem<NW>) / 4);
+	u32 *mtab = reinterpret_cast<u32 *>(smem_raw) + WALK_WARPS * WPW * (sizeof(WalkerSmem<NW>) / 4);
 	const int L = a.L;
 	for (int i = threadIdx.x; i < 2 * a.maxmatch * W2; i += WALK_WARPS * 32) {
 		const int row = i / W2, k = i % W2, rv = row >= a.maxmatch, j = rv ? row - a.maxmatch : row;
 		const int mlo = rv ? 2 * j : 0, mhi = rv ? 2 * L : 2 * (L - j);
 		mtab[i] = lowmask32(mhi - 32 * k) & ~lowmask32(mlo - 32 * k);
 	}
-	if (lane < NW) s.zpad[lane] = 0u;
-	if (lane < 2) { s.zpad2[lane] = 0u; s.zpad3[lane] = 0u; }
+	if (sub < NW) s.zpad[sub] = 0u;
+	if (sub < 2) { s.zpad2[sub] = 0u; s.zpad3[sub] = 0u; }
 	__syncthreads();
 
 	u32 c_steps = 0, c_probes = 0, c_hits = 0, c_cmp = 0, c_fail = 0, c_restart = 0;
@@ -302,7 +313,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
 		a.lrecs[(size_t)s.lchunk * CHUNK + s.lfill++] = rec;
 	};
 
-	// walker state: identical in all lanes of the warp (every update comes from a broadcast value)
+	// walker state: identical in all lanes of the walker's group (every update comes from a broadcast value)
 	int state = S_DONE, head = 0, jb = 0, dry = 0;
 	bool left_mode = false, prev_unmatched = false;
 	u32 current = 0, prev = 0;
@@ -312,20 +323,20 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
 		s.stripe = wid; s.stripes_tried = 0;
 		s.cursor = wid < a.walkers ? (long long)((((u64)wid + 1) * a.n_loc) / a.walkers) - 1 : -1;
 	}
-	__syncwarp();
+	__syncwarp(gmask);
 	if (wid < a.walkers) {
 		// reorder.cpp:476-497: walker t starts at read t*(n/T).  (The reference thread gives up if that read is taken;
 		// here the walker looks for another head instead.)
 		const u32 start = a.base + (u32)((u64)wid * (a.n_loc / a.walkers));
 		int ok = leader ? (int)try_claim(a, start) : 0;
-		ok = __shfl_sync(FULL, ok, 0);
+		ok = __shfl_sync(gmask, ok, gbase);
 		if (ok) { current = start; state = S_NEWHEAD; c_restart += leader; }
 		else state = S_RESTART;
 	}
 
 	// lane constants: probe kind and shift inside a round
-	const int kind = lane & 3;   // 0: fwd dict0, 1: fwd dict1, 2: rev dict0, 3: rev dict1 (reorder.cpp:517-643 order)
-	const int jq = lane >> 2;
+	const int kind = sub & 3;    // 0: fwd dict0, 1: fwd dict1, 2: rev dict0, 3: rev dict1 (reorder.cpp:517-643 order)
+	const int jq = sub >> 2;
 	const bool rev = kind >= 2;
 	const int l = kind & 1;
 	const DictView dv = a.d[l];
@@ -334,7 +345,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
 	const int step2 = rev ? -2 : 2;       // a shift by one base moves this lane's windows by step2 bits
 	const u32 *wbase = rev ? s.rref : s.ref;
 	const u32 *mbase = mtab + (rev ? a.maxmatch * W2 : 0);
-	// bit r of vmask: this lane's probe exists in the round that starts at shift 8r (reorder.cpp:520-523, 585-588)
+	// bit r of vmask: this lane's probe exists in the round that starts at shift SPR*r (reorder.cpp:520-523, 585-588)
 	u32 vmask = 0;
 	for (int r = 0; SPR * r < a.maxmatch; r++) {
 		const int j = SPR * r + jq;
@@ -353,7 +364,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
 		h = slot_hash(key) & dv.slot_mask & ~1u;
 	};
 	auto issue = [&](int j, Probe &p) {
-		p.pend = (vmask >> (j >> 3)) & 1u;
+		p.pend = (vmask >> (j >> SPR_LOG)) & 1u;
 		p.home = true;
 		if (p.pend) {
 			probe_key(j, p.key, p.h);
@@ -365,7 +376,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
 
 	// L2 prefetch of the bucket that the probe for shift j will read (used one round ahead in a fruitless search)
 	auto prefetch = [&](int j) {
-		if ((vmask >> (j >> 3)) & 1u) {
+		if ((vmask >> (j >> SPR_LOG)) & 1u) {
 			u64 key;
 			u32 h;
 			probe_key(j, key, h);
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
 	Probe pc;
 	pc.pend = false;
 
-	while (state != S_DONE) {
+	while (__any_sync(FULL, state != S_DONE)) {
 		PROF_T0();
 		// ---- new chain head (reorder.cpp:650-688).  The reference takes the highest unclaimed index through a private
 		// downward cursor per thread.  Here the reads are cut into one stripe per walker; a walker scans its own stripe
@@ -390,14 +401,14 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
 				if (cursor < slo) {
 					// stripe exhausted: everything in it is claimed for good
 					if (leader) a.stripe_done[stripe] = 1u;
-					// move to the next stripe (cyclically) that is not known to be finished, 32 flags at a time
+					// move to the next stripe (cyclically) that is not known to be finished, G flags at a time
 					bool found_stripe = false;
 					while (tried + 1 < a.walkers) {
-						const u32 span = min(32u, a.walkers - 1 - tried);
-						u32 cs = stripe + 1 + lane;
+						const u32 span = min((u32)G, a.walkers - 1 - tried);
+						u32 cs = stripe + 1 + sub;
 						if (cs >= a.walkers) cs -= a.walkers;
-						const bool open_ = (u32)lane < span && ldvol(&a.stripe_done[cs]) == 0u;
-						const u32 bal = __ballot_sync(FULL, open_);
+						const bool open_ = (u32)sub < span && ldvol(&a.stripe_done[cs]) == 0u;
+						const u32 bal = __ballot_sync(gmask, open_) >> gbase;
 						if (bal) {
 							const u32 f = __ffs(bal) - 1;
 							stripe = stripe + 1 + f;
@@ -415,18 +426,18 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
 					continue;
 				}
 				const long long topw = cursor >> 5;
-				const long long wi = topw - lane;
+				const long long wi = topw - sub;
 				u32 word = (wi >= 0 && wi >= (slo >> 5)) ? ldvol(&a.claim[wi]) : 0u;
-				if (lane == 0) { int bt = (int)(cursor & 31); if (bt != 31) word &= (2u << bt) - 1u; }
+				if (sub == 0) { int bt = (int)(cursor & 31); if (bt != 31) word &= (2u << bt) - 1u; }
 				if (wi == (slo >> 5)) word &= ~((1u << (slo & 31)) - 1u);
-				const u32 bal = __ballot_sync(FULL, word != 0u);
-				if (!bal) { cursor = (topw - 31) * 32 - 1; continue; }
+				const u32 bal = __ballot_sync(gmask, word != 0u) >> gbase;
+				if (!bal) { cursor = (topw - (G - 1)) * 32 - 1; continue; }
 				const int src = __ffs(bal) - 1;
-				const u32 wv = __shfl_sync(FULL, word, src);
+				const u32 wv = __shfl_sync(gmask, word, gbase + src);
 				const int bit = 31 - __clz(wv);
 				const u32 j = (u32)((topw - src) * 32 + bit);
 				int got = leader ? (int)try_claim(a, a.base + j) : 0;
-				got = __shfl_sync(FULL, got, 0);
+				got = __shfl_sync(gmask, got, gbase);
 				cursor = (long long)j - 1; // j is claimed now, by this walker or by another one
 				if (got) { current = a.base + j; got_head = true; break; }
 			}
@@ -435,7 +446,6 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
 			else {
 				state = S_DONE;
 				if (leader && s.chunk != NONE) a.chunk_fill[s.chunk] = s.fill;
-				break;
 			}
 		}
 		PROF_ADD(0);
@@ -444,11 +454,11 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
 		// walk starts on the reverse-complement strand.  A walker whose last heads all stayed alone (the tail of the job,
 		// where the unclaimed reads are the ones no dictionary window finds) goes right only.
 		if (state == S_NEWHEAD) {
-			__syncwarp();
-			if (lane < W2) s.cur[lane] = __ldg(reinterpret_cast<const u32 *>(a.reads + (size_t)current * NW) + lane);
-			__syncwarp();
+			__syncwarp(gmask);
+			if (sub < W2) s.cur[sub] = __ldg(reinterpret_cast<const u32 *>(a.reads + (size_t)current * NW) + sub);
+			__syncwarp(gmask);
 			left_mode = a.extend != 0 && dry < DRY_HEADS;
-			update_ref<NW>(s, L, lane, true, left_mode, 0, head);
+			update_ref<NW, G>(s, L, sub, gmask, true, left_mode, 0, head);
 			prev = current;
 			prev_unmatched = true;
 			jb = 0;
@@ -506,22 +516,22 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
 						if (hamming<NW>(hw, hr, hm, rw) <= a.thresh) { cand = rid; ps = P_CAND; break; }
 					}
 				}
-				const u32 bc = __ballot_sync(FULL, ps == P_CAND), bp = __ballot_sync(FULL, ps == P_PENDING);
+				const u32 bc = __ballot_sync(gmask, ps == P_CAND) >> gbase, bp = __ballot_sync(gmask, ps == P_PENDING) >> gbase;
 				if (!(bc | bp)) break; // nothing matches in these shifts
 				if (bc && (!bp || (bc & (0u - bc)) < (bp & (0u - bp)))) {
 					const int win = __ffs(bc) - 1;
 					int got = 0;
-					if (lane == win) {
+					if (sub == win) {
 						got = try_claim(a, cand);
 						if (!got) { c_fail++; ps = P_BIN; }
 					}
-					got = __shfl_sync(FULL, got, win);
+					got = __shfl_sync(gmask, got, gbase + win);
 					if (got) {
 						found = true;
-						k_rid = __shfl_sync(FULL, cand, win);
+						k_rid = __shfl_sync(gmask, cand, gbase + win);
 						k_j = jb + (win >> 2);
 						k_rev = (win & 3) >= 2;
-						if (lane == win) {
+						if (sub == win) {
 #pragma unroll
 							for (int k = 0; k < W2; k++) s.cur[k] = rw[k];
 						}
@@ -537,8 +547,8 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
 			if (found) {
 				// ---- a read was appended (reorder.cpp:560-578 / 624-641)
 				current = k_rid;
-				__syncwarp();
-				update_ref<NW>(s, L, lane, false, k_rev != 0, k_j, head);
+				__syncwarp(gmask);
+				update_ref<NW, G>(s, L, sub, gmask, false, k_rev != 0, k_j, head);
 				if (leader) {
 					if (!left_mode) {
 						if (prev_unmatched) emit(mkrec(prev, (u32)L, 0, 0, 0));
@@ -568,18 +578,18 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
 		if (state == S_CHAINEND) {
 			if (left_mode) {
 				// the left run ends: write it in front of the head, last found first, then walk right from the head
-				__syncwarp();
+				__syncwarp(gmask);
 				const u32 k = s.lcount;
 				if (k > 0) {
 					if (leader) lemit(mkrec(s.pend, (u32)L, s.pend_f ^ 1u, 0, 0)); // leftmost read = head of the chain
-					__syncwarp();
+					__syncwarp(gmask);
 					u32 c = s.lchunk, f = s.lfill, remaining = k;
 					while (remaining) {
-						const u32 take = min(min(f, 32u), remaining);
+						const u32 take = min(min(f, (u32)G), remaining);
 						u64 r = 0;
-						if ((u32)lane < take) r = __ldcg(&a.lrecs[(size_t)c * CHUNK + f - 1 - lane]);
+						if ((u32)sub < take) r = __ldcg(&a.lrecs[(size_t)c * CHUNK + f - 1 - sub]);
 						for (u32 t = 0; t < take; t++) {
-							const u64 rr = __shfl_sync(FULL, r, t);
+							const u64 rr = __shfl_sync(gmask, r, gbase + t);
 							if (leader) emit(rr);
 						}
 						f -= take;
@@ -594,10 +604,10 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, MB) walk_kernel(WalkArgs a)
 				}
 				left_mode = false;
 				current = prev;
-				__syncwarp();
-				if (lane < W2) s.cur[lane] = __ldg(reinterpret_cast<const u32 *>(a.reads + (size_t)current * NW) + lane);
-				__syncwarp();
-				update_ref<NW>(s, L, lane, true, false, 0, head);
+				__syncwarp(gmask);
+				if (sub < W2) s.cur[sub] = __ldg(reinterpret_cast<const u32 *>(a.reads + (size_t)current * NW) + sub);
+				__syncwarp(gmask);
+				update_ref<NW, G>(s, L, sub, gmask, true, false, 0, head);
 				jb = 0;
 				state = S_SEARCH;
 			} else {
@@ -687,55 +697,56 @@ __global__ void __launch_bounds__(256) chunk_gather_kernel(const u64 *__restrict
 	}
 }
 
-template <int NW>
+template <int NW, int G>
 size_t walk_smem(const WalkArgs &a)
 {
-	return sizeof(WalkerSmem<NW>) * WALK_WARPS + (size_t)2 * a.maxmatch * 2 * NW * sizeof(u32);
+	return sizeof(WalkerSmem<NW>) * WALK_WARPS * (32 / G) + (size_t)2 * a.maxmatch * 2 * NW * sizeof(u32);
 }
-template <int NW, int MB>
+template <int NW, int G>
 int launch_walk(harcgpu_ctx *c, const WalkArgs &a)
 {
-	const size_t smem = walk_smem<NW>(a);
-	CK(cudaFuncSetAttribute(walk_kernel<NW, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	walk_kernel<NW, MB><<<KL + cdiv(a.walkers, WALK_WARPS), WALK_WARPS * 32, smem, c->st>>>(a);
+	constexpr int WPB = WALK_WARPS * 32 / G; // walkers per block
+	const size_t smem = walk_smem<NW, G>(a);
+	CK(cudaFuncSetAttribute(walk_kernel<NW, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	walk_kernel<NW, G><<<KL + cdiv(a.walkers, WPB), WALK_WARPS * 32, smem, c->st>>>(a);
 	CK(cudaGetLastError());
 	return 0;
 }
 
 // walkers that can be resident at once: a walker that is not resident only starts after the others have finished
-template <int NW, int MB>
+template <int NW, int G>
 int resident_walkers(harcgpu_ctx *c, const WalkArgs &a, u32 *out)
 {
-	const size_t smem = walk_smem<NW>(a);
+	constexpr int WPB = WALK_WARPS * 32 / G;
+	const size_t smem = walk_smem<NW, G>(a);
 	int nb = 0, sms = 0;
-	CK(cudaFuncSetAttribute(walk_kernel<NW, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, walk_kernel<NW, MB>, WALK_WARPS * 32, smem));
+	CK(cudaFuncSetAttribute(walk_kernel<NW, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, walk_kernel<NW, G>, WALK_WARPS * 32, smem));
 	CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-	*out = (u32)nb * (u32)sms * WALK_WARPS;
+	*out = (u32)nb * (u32)sms * WPB;
 	return 0;
 }
 } // namespace
 
-// reads of up to 128 bases (NW <= 4) come in three register budgets, longer ones in one
-#define DISPATCH_NW(NWv, MBv, CALL)                                                         \
-	switch ((NWv) * 100 + ((NWv) <= 4 ? (MBv) : 4)) {                                       \
-	case 108: { constexpr int NW = 1, MB = 8; CALL; } break;                                \
-	case 208: { constexpr int NW = 2, MB = 8; CALL; } break;                                \
-	case 308: { constexpr int NW = 3, MB = 8; CALL; } break;                                \
-	case 408: { constexpr int NW = 4, MB = 8; CALL; } break;                                \
-	case 110: { constexpr int NW = 1, MB = 10; CALL; } break;                               \
-	case 210: { constexpr int NW = 2, MB = 10; CALL; } break;                               \
-	case 310: { constexpr int NW = 3, MB = 10; CALL; } break;                               \
-	case 410: { constexpr int NW = 4, MB = 10; CALL; } break;                               \
-	case 112: { constexpr int NW = 1, MB = 12; CALL; } break;                               \
-	case 212: { constexpr int NW = 2, MB = 12; CALL; } break;                               \
-	case 312: { constexpr int NW = 3, MB = 12; CALL; } break;                               \
-	case 412: { constexpr int NW = 4, MB = 12; CALL; } break;                               \
-	case 504: { constexpr int NW = 5, MB = 4; CALL; } break;                                \
-	case 604: { constexpr int NW = 6, MB = 4; CALL; } break;                                \
-	case 704: { constexpr int NW = 7, MB = 4; CALL; } break;                                \
-	case 804: { constexpr int NW = 8, MB = 4; CALL; } break;                                \
-	default: harcgpu_set_error("unsupported read length %d / walk variant %d", c->L, (int)(MBv)); return -1; \
+#define DISPATCH_NW_G(NWv, Gv, CALL)                                                         \
+	switch ((NWv) * 100 + (Gv)) {                                                            \
+	case 116: { constexpr int NW = 1, G = 16; CALL; } break;                                 \
+	case 216: { constexpr int NW = 2, G = 16; CALL; } break;                                 \
+	case 316: { constexpr int NW = 3, G = 16; CALL; } break;                                 \
+	case 416: { constexpr int NW = 4, G = 16; CALL; } break;                                 \
+	case 516: { constexpr int NW = 5, G = 16; CALL; } break;                                 \
+	case 616: { constexpr int NW = 6, G = 16; CALL; } break;                                 \
+	case 716: { constexpr int NW = 7, G = 16; CALL; } break;                                 \
+	case 816: { constexpr int NW = 8, G = 16; CALL; } break;                                 \
+	case 132: { constexpr int NW = 1, G = 32; CALL; } break;                                 \
+	case 232: { constexpr int NW = 2, G = 32; CALL; } break;                                 \
+	case 332: { constexpr int NW = 3, G = 32; CALL; } break;                                 \
+	case 432: { constexpr int NW = 4, G = 32; CALL; } break;                                 \
+	case 532: { constexpr int NW = 5, G = 32; CALL; } break;                                 \
+	case 632: { constexpr int NW = 6, G = 32; CALL; } break;                                 \
+	case 732: { constexpr int NW = 7, G = 32; CALL; } break;                                 \
+	case 832: { constexpr int NW = 8, G = 32; CALL; } break;                                 \
+	default: harcgpu_set_error("unsupported read length %d / lanes per walker %d", c->L, (int)(Gv)); return -1; \
 	}
 
 int s1_init_claim(harcgpu_ctx *c, u32 *claim, u32 n)
@@ -764,13 +775,14 @@ int s1_reorder(harcgpu_ctx *c)
 	// heads), capped at what is resident at once.
 	u32 resident = 0;
 	int rc = -1;
-	if (c->p.lanes_per_walker != 0 && c->p.lanes_per_walker != 32) { harcgpu_set_error("lanes_per_walker: a walker is one warp (0 or 32)"); return -1; }
+	int lanes = c->p.lanes_per_walker;
+	if (const char *e = getenv("HARCGPU_LANES")) lanes = atoi(e); // tuning aid
+	if (lanes == 0) lanes = 32;
+	if (lanes != 16 && lanes != 32) { harcgpu_set_error("lanes_per_walker must be 16 or 32"); return -1; }
 	if (c->p.maxmatch < 1 || c->p.maxmatch > 16 * c->NW) { harcgpu_set_error("maxmatch %d out of range for read length %d", c->p.maxmatch, c->L); return -1; }
 	WalkArgs a;
 	a.maxmatch = c->p.maxmatch;
-	int mb = 8;
-	if (const char *e = getenv("HARCGPU_WALK_MB")) mb = atoi(e); // tuning aid: 8, 10 or 12 blocks per SM
-	DISPATCH_NW(c->NW, mb, (rc = resident_walkers<NW, MB>(c, a, &resident)));
+	DISPATCH_NW_G(c->NW, lanes, (rc = resident_walkers<NW, G>(c, a, &resident)));
 	if (rc) return rc;
 	// one job on several GPUs: this GPU's walkers own the id range [base, base + n_loc) for starts and restarts
 	const bool sharded = c->shard_world > 1;
@@ -822,7 +834,7 @@ int s1_reorder(harcgpu_ctx *c)
 	a.lrecs = lrecs; a.lprev = lprev; a.lchunk_ctr = ctrs + 1; a.max_lchunks = max_chunks;
 	a.counters = c->counters;
 	c->tic();
-	DISPATCH_NW(c->NW, mb, (rc = launch_walk<NW, MB>(c, a)));
+	DISPATCH_NW_G(c->NW, lanes, (rc = launch_walk<NW, G>(c, a)));
 	if (rc) return rc;
 	c->toc("walk");
 	CK(cudaGetLastError());
