@@ -377,7 +377,7 @@ def main():
         "stage1": {"matched": m, "singletons": s, "chain_heads": u, "probes_per_read": cnt["probes"] / max(1, cnt["steps"]),
                    "compares_per_read": cnt["compares"] / max(1, cnt["steps"]), "claim_fails": cnt["claim_fails"]},
         "stage2": {"aligned_singletons": es.aligned_singletons, "aligned_N": es.aligned_N},
-        "roofline": {"bound": "hbm", "kernel": "walk_kernel<4, 8> (one walker per warp)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "walk_kernel<4, 32> (one walker per warp)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,
                      "algorithmic_bytes_per_clean_read": balg, "model_probes_per_read": P,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
