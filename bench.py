@@ -183,6 +183,8 @@ def main():
                     help="N>1: read-sets = every rank compresses its own read set (weak scaling, no data-path collective); "
                          "single-job = ONE read set of --reads on all ranks (strong scaling: shared claim bitmap over NVLink peer "
                          "memory, all-gather of singleton ids, all-reduce(min) of pool claims)")
+    ap.add_argument("--shard-dicts", type=int, default=0,
+                    help="single-job mode: 1 = dictionaries sharded by key hash over the GPUs (probed through NVLink peer memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer pass")
     ap.add_argument("--ingest-reads", type=float, default=8e6,
@@ -232,7 +234,8 @@ def main():
     del w["all"]
 
     ctx = harc_b200.HarcGpu(L, device=local, walkers=args.walkers, file_sets=args.file_sets,
-                            reads_per_walker=args.reads_per_walker, extend=args.extend)
+                            reads_per_walker=args.reads_per_walker, extend=args.extend,
+                            shard_dicts=args.shard_dicts if single_job else 0)
     stream = torch.cuda.ExternalStream(ctx.stream())
     phases = ["pack", "dict", "walk", "finalize", "pooldict", "encode"]
 
@@ -370,7 +373,7 @@ def main():
         "config": {"workload": "configs[1]: %d x %dbp reads, 1%% substitutions incl. N (gen_fastq_noRC -e model), %d bp synthetic genome, %s"
                                % (args.reads, L, args.genome, "ONE read set on all GPUs" if single_job else "per GPU"),
                    "reads_per_gpu": args.reads, "clean_reads": n_clean, "reads_with_N": n_N, "walkers": ctx.p.walkers or "auto",
-                   "file_sets": args.file_sets, "parallelism": ("single GPU" if world == 1 else "one job: claim bitmap in NVLink peer memory + all-gather/all-reduce(min) of pool claims"
+                   "file_sets": args.file_sets, "parallelism": ("single GPU" if world == 1 else ("one job: claim bitmap%s in NVLink peer memory + all-gather/all-reduce(min) of pool claims" % (" and dictionary shards" if args.shard_dicts else ""))
                                    if single_job else "1 independent read set per GPU"),
                    "l2": "inputs (%.1f GB ASCII, %.1f GB packed) exceed the 126 MB L2; no explicit flush" % ((n_clean + n_N) * 101 / 1e9, n_clean * 32 / 1e9)},
         "phases_ms": ph,

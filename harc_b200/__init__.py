@@ -30,7 +30,8 @@ class Params(ctypes.Structure):
     _fields_ = [("readlen", ctypes.c_int), ("maxmatch", ctypes.c_int), ("thresh", ctypes.c_int), ("thresh_s", ctypes.c_int),
                 ("numdict", ctypes.c_int), ("maxsearch", ctypes.c_int), ("dict_start", ctypes.c_int * 2),
                 ("dict_end", ctypes.c_int * 2), ("walkers", ctypes.c_int), ("file_sets", ctypes.c_int),
-                ("reads_per_walker", ctypes.c_int), ("extend", ctypes.c_int), ("lanes_per_walker", ctypes.c_int)]
+                ("reads_per_walker", ctypes.c_int), ("extend", ctypes.c_int), ("lanes_per_walker", ctypes.c_int),
+                ("shard_dicts", ctypes.c_int)]
 
 
 class EncodeSizes(ctypes.Structure):
@@ -126,7 +127,7 @@ class HarcError(RuntimeError):
     pass
 
 
-def default_params(readlen, walkers=0, file_sets=1, reads_per_walker=0, extend=0, lanes_per_walker=0):
+def default_params(readlen, walkers=0, file_sets=1, reads_per_walker=0, extend=0, lanes_per_walker=0, shard_dicts=0):
     lib = load_library()
     p = Params()
     if lib.harcgpu_default_params(int(readlen), ctypes.byref(p)):
@@ -136,6 +137,7 @@ def default_params(readlen, walkers=0, file_sets=1, reads_per_walker=0, extend=0
     p.reads_per_walker = reads_per_walker
     p.extend = extend
     p.lanes_per_walker = lanes_per_walker
+    p.shard_dicts = shard_dicts
     return p
 
 
@@ -154,9 +156,10 @@ class HarcGpu:
     """One context on one GPU.  Method names follow include/harcgpu.h."""
 
     def __init__(self, readlen=None, device=0, params=None, walkers=0, file_sets=1, reads_per_walker=0, extend=0,
-                 lanes_per_walker=0):
+                 lanes_per_walker=0, shard_dicts=0):
         self.lib = load_library()
-        self.p = params if params is not None else default_params(readlen, walkers, file_sets, reads_per_walker, extend, lanes_per_walker)
+        self.p = params if params is not None else default_params(readlen, walkers, file_sets, reads_per_walker, extend, lanes_per_walker,
+                                                                  shard_dicts)
         self.L = self.p.readlen
         h = ctypes.c_void_p()
         self._ck(self.lib.harcgpu_create(device, ctypes.byref(self.p), ctypes.byref(h)))

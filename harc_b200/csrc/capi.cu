@@ -216,9 +216,18 @@ int harcgpu_build_dicts(harcgpu_ctx *c)
 	if (!c || !c->reads) { harcgpu_set_error("load reads first"); return -1; }
 	CK(cudaSetDevice(c->device));
 	c->tic();
-	for (int l = 0; l < c->p.numdict; l++)
-		if (build_dict(c, c->d1[l], c->reads, nullptr, c->n, c->NW, c->p.dict_start[l], c->p.dict_end[l], 2))
+	if (c->dicts_sharded && c->shard_n != c->n) { harcgpu_set_error("sharded dictionaries: harcgpu_shard_init was called for %u reads, %u are loaded", c->shard_n, c->n); return -1; }
+	for (int l = 0; l < c->p.numdict; l++) {
+		DictShard sh;
+		if (c->dicts_sharded) {
+			char *arena = (char *)c->seg[c->shard_rank];
+			sh.rank = c->shard_rank; sh.world = c->shard_world; sh.cap = c->shard_cap;
+			sh.slots = (ulonglong2 *)(arena + c->arena_slots_off[l]);
+			sh.ids = (u32 *)(arena + c->arena_ids_off[l]);
+		}
+		if (build_dict(c, c->d1[l], c->reads, nullptr, c->n, c->NW, c->p.dict_start[l], c->p.dict_end[l], 2, c->dicts_sharded ? &sh : nullptr))
 			return -1;
+	}
 	c->toc("dict");
 	c->dicts_built = true;
 	return 0;
@@ -260,6 +269,11 @@ static void shard_close(harcgpu_ctx *c)
 		c->seg[r] = nullptr; c->seg_opened[r] = false;
 	}
 	c->shard_world = 1; c->shard_rank = 0; c->shard_n = 0; c->seg_per = 0; c->shard_ready = false;
+	if (c->dicts_sharded) {
+		for (int l = 0; l < 2; l++) free_dict(c, c->d1[l]); // their slots / ids pointed into the arena
+		c->dicts_built = false;
+	}
+	c->dicts_sharded = false; c->shard_cap = 0;
 }
 
 int harcgpu_shard_init(harcgpu_ctx *c, int rank, int world, uint32_t n_total, void *ipc_handle_out)
@@ -271,7 +285,26 @@ int harcgpu_shard_init(harcgpu_ctx *c, int rank, int world, uint32_t n_total, vo
 	c->shard_rank = rank; c->shard_world = world; c->shard_n = n_total;
 	c->seg_per = (uint32_t)((((uint64_t)n_total + world - 1) / world + 31) / 32 * 32);
 	if (c->seg_per == 0) c->seg_per = 32;
-	if (c->alloc(&c->seg[rank], (size_t)c->seg_per / 32)) return -1;
+	// arena of this GPU: its bitmap range, then per dictionary its shard of the key table and room for its id lists
+	auto round256 = [](size_t b) { return (b + 255) / 256 * 256; };
+	size_t off = round256((size_t)c->seg_per / 8);
+	c->dicts_sharded = c->p.shard_dicts != 0 && world > 1;
+	if (c->dicts_sharded) {
+		const u64 per = ((u64)n_total + world - 1) / world;
+		u64 cap = 16;
+		while (cap < 2 * per + per / 4 + 1024) cap <<= 1; // load factor <= 0.45 even for a shard 10 % above the mean
+		if (cap > 0x80000000ull) { harcgpu_set_error("dictionary shard too large"); return -1; }
+		c->shard_cap = (u32)cap;
+		for (int l = 0; l < c->p.numdict; l++) {
+			c->arena_slots_off[l] = off; off += (size_t)cap * sizeof(ulonglong2);
+			c->arena_ids_off[l] = off;   off += round256((size_t)n_total * 4); // worst case: every read in one shard
+		}
+		for (int l = 0; l < 2; l++) free_dict(c, c->d1[l]);
+		c->dicts_built = false;
+	}
+	char *arena = nullptr;
+	if (c->alloc(&arena, off)) return -1;
+	c->seg[rank] = (u32 *)arena;
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
 	cudaIpcMemHandle_t h;
 	CK(cudaIpcGetMemHandle(&h, c->seg[rank]));

@@ -47,12 +47,14 @@ __device__ __forceinline__ u32 slot_hash(u64 x)
 	x *= 0x9E3779B97F4A7C15ull;
 	return (u32)(x >> 32) ^ (u32)x;
 }
+struct DictView;
 
 // One dictionary: canonical CSR (keys ascending, ids ascending inside a bin: reorder.cpp:344-391) plus an
 // open-addressing table key -> bin.  A slot is 16 bytes {key, val}: val == 0 = empty, else size = bits 32..62 and the low
 // half is the bin's first index into ids[] -- or, for a bin of one read (most bins), the read id itself, so that the
 // common probe needs no second dependent load.
 struct DictDev {
+	bool external = false;    // slots and ids live in the shard arena (one job on several GPUs): not owned
 	u64 *keys = nullptr;      // [numkeys] ascending
 	u32 *start = nullptr;     // [numkeys+1]
 	u32 *ids = nullptr;       // [n]
@@ -66,7 +68,16 @@ struct DictView {
 	const u32 *ids;
 	u32 slot_mask;
 	int dstart, dend; // in bases
+	// one job on several GPUs with sharded dictionaries: shard s of the table and of the id lists (peer memory), every
+	// shard with slot_mask + 1 slots; world == 0 otherwise
+	const ulonglong2 *sslots[8];
+	const u32 *sids[8];
+	int world;
 };
+// 64-bit product behind slot_hash; the shard of a key comes from bits the slot index does not use
+__device__ __host__ __forceinline__ u64 key_mix(u64 x) { return x * 0x9E3779B97F4A7C15ull; }
+__device__ __host__ __forceinline__ u32 mix_slot(u64 m) { return (u32)(m >> 32) ^ (u32)m; }
+__device__ __host__ __forceinline__ u32 mix_shard(u64 m, int world) { return (u32)((((m >> 40) & 0xffffffull) * (u64)world) >> 24); }
 
 // Slots are probed in buckets of two (one 32-byte sector): a key hashes to an even slot (its home bucket) and is inserted
 // into the first empty slot from there on.  A key that did not fit into its home bucket sets the OVERFLOW bit (bit 63 of

@@ -37,7 +37,13 @@ struct harcgpu_ctx {
 	// one job on several GPUs (harcgpu_shard_*): claim bitmap cut into contiguous id ranges, one per GPU
 	int shard_rank = 0, shard_world = 1;
 	u32 shard_n = 0, seg_per = 0;
+	// One allocation per GPU ("arena": its bitmap range, then per dictionary its shard of the key table and of the id
+	// lists), so that one IPC handle per GPU is exchanged; seg[r] = bitmap range of GPU r = start of arena r.
 	u32 *seg[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // seg[shard_rank] is local
+	bool dicts_sharded = false;
+	u32 shard_cap = 0;                    // slots per dictionary shard (power of two)
+	size_t arena_slots_off[2] = { 0, 0 }; // byte offsets inside an arena
+	size_t arena_ids_off[2] = { 0, 0 };
 	bool seg_opened[8] = { false, false, false, false, false, false, false, false };
 	bool shard_ready = false;
 	int (*pool_exchange)(void *user, void *d_best, uint64_t count) = nullptr;
@@ -166,7 +172,14 @@ int s1_init_claim(harcgpu_ctx *c, u32 *claim, u32 n);
 // stage1.cu
 int s1_pack_reads(harcgpu_ctx *c, const void *d_ascii, u32 n);
 int s1_packN(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *out2, u64 *outN);
-int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, u32 n, int words, int ds, int de, int bits);
+struct DictShard { // where a dictionary shard of one job on several GPUs is built (inside the arena of ctx.h)
+	int rank, world;
+	ulonglong2 *slots;
+	u32 cap;   // slots, power of two
+	u32 *ids;  // room for every read id
+};
+int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, u32 n, int words, int ds, int de, int bits,
+               const DictShard *shard = nullptr);
 void free_dict(harcgpu_ctx *c, DictDev &d);
 int s1_reorder(harcgpu_ctx *c);
 int s1_unpack_reads(harcgpu_ctx *c, const u64 *reads, const u32 *order, const u8 *rev, u32 cnt, char *d_out);

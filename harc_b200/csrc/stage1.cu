@@ -9,6 +9,7 @@
 // Data layout in HBM: reads[n][NW] u64 (NW = ceil(2L/64)); per dictionary the canonical CSR (keys, start, ids) and a
 // 16-byte-slot open-addressing table at load factor <= 0.5; a claim bitmap (1 bit/read); a chunked record log.
 #include "ctx.h"
+#include <utility>
 #include <cub/device/device_radix_sort.cuh>
 
 // ------------------------------------------------------------------------------------------------ K1 pack
@@ -203,25 +204,51 @@ int s1_unpack_reads(harcgpu_ctx *c, const u64 *reads, const u32 *order, const u8
 
 void free_dict(harcgpu_ctx *c, DictDev &d)
 {
-	c->release(d.keys); c->release(d.start); c->release(d.ids); c->release(d.slots);
+	c->release(d.keys); c->release(d.start);
+	if (!d.external) { c->release(d.ids); c->release(d.slots); }
 	d = DictDev();
 }
 
+namespace {
+// one job on several GPUs, sharded dictionaries: keep the (key, id) pairs whose key hashes to this GPU's shard
+__global__ void __launch_bounds__(256) shard_flag_kernel(const u64 *__restrict__ keys, u32 n, int rank, int world, u32 *__restrict__ flag)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) flag[i] = mix_shard(key_mix(keys[i]), world) == (u32)rank ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) shard_compact_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ ids, const u32 *__restrict__ flag,
+                                                            const u32 *__restrict__ ex, u32 n, u64 *__restrict__ k_out, u32 *__restrict__ id_out)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n && flag[i]) { k_out[ex[i]] = keys[i]; id_out[ex[i]] = ids[i]; }
+}
+} // namespace
+
 // bits == 2: stage I key = bits [2*ds, 2*(de+1)) of the packed read; bits == 3: stage II key from (reads, readsN)
-int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, u32 n, int words, int ds, int de, int bits)
+// shard != nullptr (stage I of one job on several GPUs): only the keys of this GPU's shard are kept; the table and
+// the id lists are built in place in the arena the peers have mapped.
+int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, u32 n, int words, int ds, int de, int bits,
+               const DictShard *shard)
 {
 	cudaStream_t st = c->st;
 	free_dict(c, d);
+	if (shard) {
+		d.external = true;
+		d.ids = shard->ids;
+		d.slots = shard->slots;
+		d.slot_mask = shard->cap - 1;
+	}
 	const int bitpos = bits * ds, nbits = bits * (de - ds + 1);
 	d.bitpos = bitpos; d.nbits = nbits;
 	u64 *k_in = nullptr, *k_out = nullptr, *scan_tmp = nullptr;
 	u32 *id_in = nullptr, *head = nullptr, *binidx = nullptr, *d_total = nullptr;
 	void *cub_tmp = nullptr;
-	if (c->alloc(&d.ids, n)) return -1;
+	if (!shard && c->alloc(&d.ids, n)) return -1;
 	if (n == 0) {
 		d.numkeys = 0;
 		if (c->alloc(&d.keys, 1) || c->alloc(&d.start, 1)) return -1;
 		CK(cudaMemsetAsync(d.start, 0, 4, st));
+		if (shard) { CK(cudaMemsetAsync(d.slots, 0, (size_t)shard->cap * sizeof(ulonglong2), st)); CK(cudaStreamSynchronize(st)); return 0; }
 		d.slot_mask = 15;
 		if (c->alloc(&d.slots, 16)) return -1;
 		CK(cudaMemsetAsync(d.slots, 0, 16 * sizeof(ulonglong2), st));
@@ -233,6 +260,35 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 	if (bits == 2) keys_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(reads, n, words, bitpos, nbits, k_in, id_in);
 	else keys3_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(reads, readsN, n, words, ds, de, k_in, id_in);
 	CK(cudaGetLastError());
+	if (shard) {
+		// keep this GPU's keys, in id order (the scan keeps the order, so ids stay ascending inside a bin)
+		u32 *flag = head, *ex = binidx, kept = 0; // both arrays are free until the sort is done
+		u64 *k_f = k_out;
+		u32 *id_f = nullptr;
+		if (c->alloc(&id_f, n)) return -1;
+		shard_flag_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(k_in, n, shard->rank, shard->world, flag);
+		CK(cudaGetLastError());
+		if (exclusive_scan_u32(flag, ex, n, scan_tmp, d_total, st)) return -1;
+		shard_compact_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(k_in, id_in, flag, ex, n, k_f, id_f);
+		CK(cudaGetLastError());
+		CK(cudaMemcpyAsync(&kept, d_total, 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		// from here on the dictionary is built over the kept pairs only
+		std::swap(k_in, k_out); // k_in = compacted keys, k_out = sort output
+		c->release(id_in);
+		id_in = id_f;
+		n = kept;
+		if (n == 0) {
+			d.numkeys = 0;
+			if (c->alloc(&d.keys, 1) || c->alloc(&d.start, 1)) return -1;
+			CK(cudaMemsetAsync(d.start, 0, 4, st));
+			CK(cudaMemsetAsync(d.slots, 0, (size_t)shard->cap * sizeof(ulonglong2), st));
+			CK(cudaStreamSynchronize(st));
+			c->release(k_in); c->release(k_out); c->release(id_in); c->release(head); c->release(binidx);
+			c->release(scan_tmp); c->release(d_total);
+			return 0;
+		}
+	}
 	size_t tb = 0;
 	CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, id_in, d.ids, (int64_t)n, 0, nbits, st));
 	if (c->alloc((char **)&cub_tmp, tb)) return -1;
@@ -249,9 +305,14 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 	bins_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(k_out, head, binidx, n, nk, d.keys, d.start);
 	CK(cudaGetLastError());
 	u64 cap = 16;
-	while (cap < 2ull * nk) cap <<= 1;
-	d.slot_mask = (u32)(cap - 1);
-	if (c->alloc(&d.slots, cap)) return -1;
+	if (shard) {
+		cap = shard->cap;
+		if ((u64)nk * 10 > cap * 9) { harcgpu_set_error("dictionary shard overflow: %u keys for %llu slots", nk, cap); return -1; }
+	} else {
+		while (cap < 2ull * nk) cap <<= 1;
+		d.slot_mask = (u32)(cap - 1);
+		if (c->alloc(&d.slots, cap)) return -1;
+	}
 	CK(cudaMemsetAsync(d.slots, 0, cap * sizeof(ulonglong2), st));
 	insert_kernel<<<KL + cdiv(nk, 256), 256, 0, st>>>(d.keys, d.start, d.ids, nk, d.slots, d.slot_mask);
 	CK(cudaGetLastError());

@@ -849,6 +849,7 @@ int s2_encode(harcgpu_ctx *c)
 		for (int l = 0; l < 2; l++) {
 			a.d[l].slots = c->d2[l].slots; a.d[l].ids = c->d2[l].ids; a.d[l].slot_mask = c->d2[l].slot_mask;
 			a.d[l].dstart = c->d2[l].bitpos / 3; a.d[l].dend = a.d[l].dstart + c->d2[l].nbits / 3 - 1;
+			a.d[l].world = 0;
 		}
 		a.L = L; a.thresh_s = c->p.thresh_s; a.maxsearch = c->p.maxsearch; a.best = best;
 		a.rank_bits = (u64)(c->shard_world > 1 ? c->shard_rank : 0) << RANK_SHIFT;

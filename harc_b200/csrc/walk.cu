@@ -363,20 +363,26 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? 8 : 4) walk_kernel(
 		key = ((u64)khi << 32) | klo;
 		h = slot_hash(key) & dv.slot_mask & ~1u;
 	};
+	// sharded dictionaries (one job on several GPUs): table and id lists of the shard that owns the key, in the owner's
+	// HBM and read over NVLink; dv.world == 0 (warp-uniform) otherwise
+	// (the per-shard pointers are indexed in the kernel parameters, not in a local copy)
+	auto slots_of = [&](u64 key) -> const ulonglong2 * { return dv.world ? a.d[l].sslots[mix_shard(key_mix(key), dv.world)] : dv.slots; };
+	auto ids_of = [&](u64 key) -> const u32 * { return dv.world ? a.d[l].sids[mix_shard(key_mix(key), dv.world)] : dv.ids; };
 	auto issue = [&](int j, Probe &p) {
 		p.pend = (vmask >> (j >> SPR_LOG)) & 1u;
 		p.home = true;
 		if (p.pend) {
 			probe_key(j, p.key, p.h);
-			p.s0 = __ldg(&dv.slots[p.h]);
-			p.s1 = __ldg(&dv.slots[p.h + 1]);
+			const ulonglong2 *sl = slots_of(p.key);
+			p.s0 = __ldg(&sl[p.h]);
+			p.s1 = __ldg(&sl[p.h + 1]);
 			c_probes++;
 		}
 	};
 
 	// L2 prefetch of the bucket that the probe for shift j will read (used one round ahead in a fruitless search)
 	auto prefetch = [&](int j) {
-		if ((vmask >> (j >> SPR_LOG)) & 1u) {
+		if (!dv.world && ((vmask >> (j >> SPR_LOG)) & 1u)) {
 			u64 key;
 			u32 h;
 			probe_key(j, key, h);
@@ -499,15 +505,16 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? 8 : 4) walk_kernel(
 					else {
 						pc.home = false;
 						pc.h = (pc.h + 2) & dv.slot_mask;
-						pc.s0 = __ldg(&dv.slots[pc.h]);
-						pc.s1 = __ldg(&dv.slots[pc.h + 1]);
+						const ulonglong2 *sl = slots_of(pc.key);
+						pc.s0 = __ldg(&sl[pc.h]);
+						pc.s1 = __ldg(&sl[pc.h + 1]);
 					}
 				}
 				if (ps == P_BIN) {
 					ps = P_DEAD;
 					while (left > 0 && seen < a.maxsearch) {
 						left--;
-						const u32 rid = bin_entry(dv, lo, size, left);
+						const u32 rid = size == 1 ? lo : __ldg(&ids_of(pc.key)[lo + left]);
 						const u32 cw = ldvol(peek_word(a, rid)); // claim bit and read are fetched together
 						load_read<NW>(a.reads, rid, rw);
 						if (!((cw >> (rid & 31)) & 1u)) continue; // removed from the bin in the reference (505-514)
@@ -825,6 +832,12 @@ int s1_reorder(harcgpu_ctx *c)
 		int ll = l < c->p.numdict ? l : 0;
 		a.d[l].slots = c->d1[ll].slots; a.d[l].ids = c->d1[ll].ids; a.d[l].slot_mask = c->d1[ll].slot_mask;
 		a.d[l].dstart = c->p.dict_start[ll]; a.d[l].dend = c->p.dict_end[ll];
+		a.d[l].world = c->dicts_sharded ? c->shard_world : 0;
+		for (int r = 0; r < 8; r++) {
+			const bool on = c->dicts_sharded && r < c->shard_world && c->seg[r];
+			a.d[l].sslots[r] = on ? (const ulonglong2 *)((const char *)c->seg[r] + c->arena_slots_off[ll]) : nullptr;
+			a.d[l].sids[r] = on ? (const u32 *)((const char *)c->seg[r] + c->arena_ids_off[ll]) : nullptr;
+		}
 		a.kbits[l] = c->d1[ll].nbits;
 	}
 	a.claim = sharded ? c->seg[c->shard_rank] : c->claim; a.hint = c->claim; a.stripe_done = stripe_done; a.walkers = walkers;

@@ -37,7 +37,9 @@ typedef struct {
 	int reads_per_walker; /* walkers == 0: one walker per this many reads, capped at what the GPU keeps resident; 0 -> 4096 */
 	int extend;        /* left extension of new chains (not in the reference; same file format): 1 on, -1 off,
 	                      0 = on when more than one walker runs (one walker without it = the reference at num_thr=1) */
-	int lanes_per_walker; /* GPU lanes that cooperate on one walker: 8, 16 or 32; 0 = default */
+	int lanes_per_walker; /* GPU lanes that cooperate on one walker: 16 or 32; 0 = default (32, one warp) */
+	int shard_dicts;   /* one job on several GPUs: 1 = both dictionaries sharded by key hash over the GPUs and probed
+	                      through NVLink peer memory (1/world of the tables per GPU), 0 = replicated on every GPU */
 } harcgpu_params;
 
 /* Sizes of everything stage II produced, so the caller can allocate before harcgpu_get_*.  (encoder.cpp:457-508) */
@@ -156,10 +158,13 @@ int harcgpu_get_globals(harcgpu_ctx *ctx, uint32_t *order, uint32_t *order_N, ui
 int harcgpu_get_packed_order(harcgpu_ctx *ctx, void *packed, uint32_t *tail, uint64_t *packed_bytes, uint32_t *tail_entries);
 
 /* ---- one job on several GPUs of one box (one process and one context per GPU) -------------------------------
- * Not in the reference (it is one process).  Every GPU holds all packed reads and both dictionaries; what is shared is
- * the claimed-read bitmap (reorder.cpp:449 remainingreads + the lock arrays of reorder.cpp:436-442): it is cut into
+ * Not in the reference (it is one process).  Every GPU holds all packed reads; the dictionaries are either replicated
+ * or, with params.shard_dicts, sharded: GPU r builds and holds the key table and the id lists of the keys whose hash
+ * falls into range r, and every walker probes the owner's table with plain loads over NVLink (the tables are read-only
+ * during the walk).  What is always shared is the claimed-read bitmap (reorder.cpp:449 remainingreads + the lock arrays of reorder.cpp:436-442): it is cut into
  * `world` contiguous id ranges, range r lives on GPU r and the other GPUs read and claim it through NVLink peer memory
- * (CUDA IPC).  GPU r's walkers start and restart only inside range r but may claim any read, so the chains of all GPUs
+ * (CUDA IPC; bitmap range and dictionary shards of a GPU live in one allocation, so one handle per GPU is exchanged).
+ * GPU r's walkers start and restart only inside range r but may claim any read, so the chains of all GPUs
  * partition the read set exactly as the threads of the reference do.  Stage II then runs per GPU on its own chains
  * (file set k = rank, encoder.cpp:169-196) against the same pool; which contig gets a pool read is settled by an
  * all-reduce(min) over the priority array, done by the caller's hook (NCCL through torch.distributed in this repo).

@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, src, dst, L):
+def _worker(rank, world, port, src, dst, L, shard_dicts):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     import torch
@@ -34,9 +34,11 @@ def _worker(rank, world, port, src, dst, L):
     out = os.path.join(src, "output")
     clean = np.fromfile(os.path.join(out, "input_clean.dna"), dtype=np.uint8)
     withN = np.fromfile(os.path.join(out, "input_N.dna"), dtype=np.uint8)
-    ctx = harc_b200.HarcGpu(L, device=rank, file_sets=1)
+    ctx = harc_b200.HarcGpu(L, device=rank, file_sets=1, shard_dicts=shard_dicts)
     res = multi.compress_sharded(ctx, dist, clean, withN)
     # a second pass on the connected context must work too (bench loop)
+    ctx.load_reads(clean)  # as the bench loop does: reload, rebuild (the shard tables are rebuilt in place), rerun
+    ctx.build_dicts()
     res = multi.fetch(ctx, multi.run_pass(ctx, dist, withN, rank, world, torch))
     multi.write_outputs(dst, rank, world, res, L, dist)
     m, s, u = res["counts"]
@@ -49,17 +51,18 @@ def _worker(rank, world, port, src, dst, L):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("shard_dicts", [0, 1], ids=["dicts_replicated", "dicts_sharded"])
 @pytest.mark.parametrize("case", [("mg100", 120000, 100, 600000, True, True)], ids=["L100_rc_err"])
-def test_one_job_on_two_gpus(workroot, case):
+def test_one_job_on_two_gpus(workroot, case, shard_dicts):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
     name, n, L, G, rc, err = case
     d = H.make_dataset(workroot, name, n, L, G, rc, err, seed=17)
-    dst = d + ".two"
+    dst = d + ".two%d" % shard_dicts
     os.makedirs(os.path.join(dst, "output"), exist_ok=True)
-    mp.spawn(_worker, args=(2, _free_port(), d, dst, L), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), d, dst, L, shard_dicts), nprocs=2, join=True)
     stats = np.load(os.path.join(dst, "stats.npy"))
     n_clean = os.path.getsize(os.path.join(d, "output", "input_clean.dna")) // (L + 1)
     n_N = os.path.getsize(os.path.join(d, "output", "input_N.dna")) // (L + 1)
@@ -70,7 +73,7 @@ def test_one_job_on_two_gpus(workroot, case):
     order_N = np.fromfile(os.path.join(dst, "output", "read_order_N_pe.bin"), dtype=np.uint32)
     assert np.array_equal(np.sort(order_N), np.arange(n_N, dtype=np.uint32))
     # single-GPU archive of the same input for the size comparison
-    one = H.clone(d, d + ".one")
+    one = H.clone(d, d + ".one%d" % shard_dicts)
     import harc_b200
     ctx = harc_b200.HarcGpu(L, file_sets=1)
     ctx.reorder_dir(one)
