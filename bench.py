@@ -201,6 +201,12 @@ def main():
             run_reference(args)
         return
 
+    # Rank 0 prints exactly ONE line on stdout, the JSON.  Everything else that writes to file descriptor 1 (NCCL's version
+    # banner, library chatter) is sent to stderr: fd 1 is pointed at stderr for the run and the JSON goes to the saved fd.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import harc_b200
     import workload as W
@@ -211,8 +217,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     # ---- workload: every rank owns an independent read set (seed differs per rank)
@@ -397,7 +401,7 @@ def main():
             out["cpu_baseline"] = cpu_baseline(args)
         except Exception as ex:  # the reference binaries are a reported baseline, never a dependency of the GPU number
             out["cpu_baseline"] = {"error": str(ex)[:200]}
-    print(json.dumps(out))
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
