@@ -26,6 +26,8 @@ constexpr int CHUNK = 32;             // records per log chunk
 constexpr u32 NONE = 0xffffffffu;
 constexpr u32 FULL = 0xffffffffu;
 constexpr int DRY_HEADS = 4;          // left extension is skipped after this many heads in a row that stayed alone
+constexpr int STREAK_HEADS = 16;      // after this many, a head is searched over STREAK_SHIFTS shifts only
+constexpr int STREAK_SHIFTS = 8;
 
 enum { S_SEARCH = 0, S_CHAINEND, S_RESTART, S_NEWHEAD, S_DONE };
 enum { P_DEAD = 0, P_PENDING, P_BIN, P_CAND };
@@ -576,7 +578,12 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? 8 : 4) walk_kernel(
 					PROF_CNT(10, 1);
 			} else {
 				jb += SPR;
-				if (jb >= a.maxmatch) state = S_CHAINEND;
+				// Tail of the job: a walker whose last heads all stayed alone is working off the reads that no dictionary
+				// window finds (errors in both windows); their neighbours are claimed, and such a head is searched over the
+				// first round of shifts only.  It is declared a singleton like any other and goes to stage II's pool.  (Not
+				// with one walker / extend off, where the walk is the reference's, shift for shift.)
+				const int jmax = (a.extend != 0 && prev_unmatched && dry >= STREAK_HEADS) ? min(a.maxmatch, STREAK_SHIFTS) : a.maxmatch;
+				if (jb >= jmax) state = S_CHAINEND;
 			}
 			PROF_ADD(4);
 		}
