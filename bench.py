@@ -179,6 +179,8 @@ def main():
     ap.add_argument("--reads-per-walker", type=int, default=0)
     ap.add_argument("--extend", type=int, default=0)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--rc", type=int, default=0, help="1: odd reads reverse-complemented (gen_fastq model, configs[2]); default gen_fastq_noRC")
+    ap.add_argument("--errors", type=int, default=1, help="0: error-free reads (configs[0])")
     ap.add_argument("--mode", default="read-sets", choices=["read-sets", "single-job"],
                     help="N>1: read-sets = every rank compresses its own read set (weak scaling, no data-path collective); "
                          "single-job = ONE read set of --reads on all ranks (strong scaling: shared claim bitmap over NVLink peer "
@@ -221,7 +223,7 @@ def main():
 
     # ---- workload: every rank owns an independent read set (seed differs per rank)
     single_job = args.mode == "single-job" and world > 1
-    w = W.make(args.reads, L, args.genome, rc=False, errors=True, seed=args.seed + (0 if single_job else 7919 * rank))
+    w = W.make(args.reads, L, args.genome, rc=bool(args.rc), errors=bool(args.errors), seed=args.seed + (0 if single_job else 7919 * rank))
     n_clean, n_N = w["n_clean"], w["n_N"]
     h_clean = torch.from_numpy(w["clean"]).pin_memory()
     h_N = torch.from_numpy(w["withN"]).pin_memory()
@@ -374,8 +376,11 @@ def main():
     out = {
         "metric": METRIC, "value": value, "unit": "Mreads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong" if single_job else "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "configs[1]: %d x %dbp reads, 1%% substitutions incl. N (gen_fastq_noRC -e model), %d bp synthetic genome, %s"
-                               % (args.reads, L, args.genome, "ONE read set on all GPUs" if single_job else "per GPU"),
+        "config": {"workload": "%s: %d x %dbp reads, %s (%s model), %d bp synthetic genome, %s"
+                               % ("configs[1]" if (args.reads, args.genome, args.rc, args.errors) == (35000000, 50000000, 0, 1) else "custom",
+                                  args.reads, L, "1% substitutions incl. N" if args.errors else "error-free",
+                                  ("gen_fastq" if args.rc else "gen_fastq_noRC") + (" -e" if args.errors else ""), args.genome,
+                                  "ONE read set on all GPUs" if single_job else "per GPU"),
                    "reads_per_gpu": args.reads, "clean_reads": n_clean, "reads_with_N": n_N, "walkers": ctx.p.walkers or "auto",
                    "file_sets": args.file_sets, "parallelism": ("single GPU" if world == 1 else ("one job: claim bitmap%s in NVLink peer memory + all-gather/all-reduce(min) of pool claims" % (" and dictionary shards" if args.shard_dicts else ""))
                                    if single_job else "1 independent read set per GPU"),
