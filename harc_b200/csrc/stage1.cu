@@ -10,7 +10,6 @@
 // 16-byte-slot open-addressing table at load factor <= 0.5; a claim bitmap (1 bit/read); a chunked record log.
 #include "ctx.h"
 #include <utility>
-#include <cub/device/device_radix_sort.cuh>
 
 // ------------------------------------------------------------------------------------------------ K1 pack
 namespace {
@@ -242,9 +241,9 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 	d.bitpos = bitpos; d.nbits = nbits;
 	u64 *k_in = nullptr, *k_out = nullptr, *scan_tmp = nullptr;
 	u32 *id_in = nullptr, *head = nullptr, *binidx = nullptr, *d_total = nullptr;
-	void *cub_tmp = nullptr;
-	if (!shard && c->alloc(&d.ids, n)) return -1;
+	u32 *id_alt = nullptr;
 	if (n == 0) {
+		if (!shard && c->alloc(&d.ids, 1)) return -1;
 		d.numkeys = 0;
 		if (c->alloc(&d.keys, 1) || c->alloc(&d.start, 1)) return -1;
 		CK(cudaMemsetAsync(d.start, 0, 4, st));
@@ -289,11 +288,12 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 			return 0;
 		}
 	}
-	size_t tb = 0;
-	CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, id_in, d.ids, (int64_t)n, 0, nbits, st));
-	if (c->alloc((char **)&cub_tmp, tb)) return -1;
 	// LSD radix sort is stable and ids start ascending, so ids stay ascending inside a bin (reorder.cpp:371-384)
-	CK(cub::DeviceRadixSort::SortPairs(cub_tmp, tb, k_in, k_out, id_in, d.ids, (int64_t)n, 0, nbits, st));
+	if (c->alloc(&id_alt, n)) return -1;
+	if (radix_sort_pairs(c, &k_in, &k_out, &id_in, &id_alt, n, 0, nbits)) return -1;
+	std::swap(k_in, k_out); // k_out = sorted keys from here on
+	if (shard) CK(cudaMemcpyAsync(d.ids, id_in, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st)); // into the arena the peers have mapped
+	else { d.ids = id_in; id_in = nullptr; }
 	heads_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(k_out, n, head);
 	CK(cudaGetLastError());
 	if (exclusive_scan_u32(head, binidx, n, scan_tmp, d_total, st)) return -1;
@@ -318,6 +318,6 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(st));
 	c->release(k_in); c->release(k_out); c->release(id_in); c->release(head); c->release(binidx);
-	c->release(scan_tmp); c->release(d_total); c->release(cub_tmp);
+	c->release(scan_tmp); c->release(d_total); c->release(id_alt);
 	return 0;
 }

@@ -17,7 +17,7 @@
 // scanned over its top 1000 ids only, without tracking removals; the result is still lossless.
 #include "ctx.h"
 #include <string.h>
-#include <cub/device/device_radix_sort.cuh>
+#include <utility>
 
 namespace {
 constexpr u32 CAP1 = 10000001u; // encoder.cpp:226: a contig is cut once list_size > 10000000
@@ -883,13 +883,10 @@ int s2_encode(harcgpu_ctx *c)
 	if (M) {
 		int end_bit = 3;
 		while (end_bit < 64 && (TOT >> (end_bit - 2)) != 0) end_bit++;
-		size_t tb = 0;
-		void *cub_tmp = nullptr;
-		CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, prio_u, iprio, rid_u, irid, (int64_t)M, 0, end_bit, st));
-		if (c->alloc((char **)&cub_tmp, tb)) return -1;
-		CK(cub::DeviceRadixSort::SortPairs(cub_tmp, tb, prio_u, iprio, rid_u, irid, (int64_t)M, 0, end_bit, st));
+		if (radix_sort_pairs(c, &prio_u, &iprio, &rid_u, &irid, M, 0, end_bit)) return -1;
+		std::swap(prio_u, iprio); // iprio / irid = sorted
+		std::swap(rid_u, irid);
 		CK(cudaStreamSynchronize(st));
-		c->release(cub_tmp);
 	}
 
 	// ---- merged list

@@ -18,7 +18,6 @@
 #include "ctx.h"
 #include <algorithm>
 #include <stdlib.h>
-#include <cub/device/device_radix_sort.cuh>
 
 namespace {
 constexpr int WALK_WARPS = 4;         // warps (= walkers) per block
@@ -881,11 +880,15 @@ int s1_reorder(harcgpu_ctx *c)
 		return -1;
 	iota_kernel<<<KL + cdiv(nchunks, 256), 256, 0, st>>>(chunk_id, nchunks);
 	CK(cudaGetLastError());
-	size_t tb = 0;
-	void *cub_tmp = nullptr;
-	CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, chunk_key, key_sorted, chunk_id, chunk_sorted, (int64_t)nchunks, 0, 64, st));
-	if (c->alloc((char **)&cub_tmp, tb)) return -1;
-	CK(cub::DeviceRadixSort::SortPairs(cub_tmp, tb, chunk_key, key_sorted, chunk_id, chunk_sorted, (int64_t)nchunks, 0, 64, st));
+	{
+		// key = walker << 32 | sequence number: two stable sorts over the bits that can be set (sequence < nchunks, walker < walkers)
+		int sb = 1, wb = 1;
+		while (sb < 32 && (nchunks >> sb) != 0) sb++;
+		while (wb < 32 && (walkers >> wb) != 0) wb++;
+		if (radix_sort_pairs(c, &chunk_key, &key_sorted, &chunk_id, &chunk_sorted, nchunks, 0, sb)) return -1;
+		if (radix_sort_pairs(c, &chunk_key, &key_sorted, &chunk_id, &chunk_sorted, nchunks, 32, 32 + wb)) return -1;
+		std::swap(chunk_id, chunk_sorted); // chunk_sorted = chunk ids in (walker, sequence) order
+	}
 	chunk_count_kernel<<<KL + cdiv((size_t)nchunks * 32, 256), 256, 0, st>>>(recs, chunk_sorted, chunk_fill, nchunks, cm, cs);
 	CK(cudaGetLastError());
 	if (exclusive_scan_u32(cm, om, nchunks, scan_tmp, totals, st)) return -1;
@@ -900,7 +903,7 @@ int s1_reorder(harcgpu_ctx *c)
 	CK(cudaStreamSynchronize(st));
 	c->toc("finalize");
 	c->n_matched = tot[0]; c->n_single = tot[1]; c->n_unmatched = (u32)cnt[5];
-	void *tmp[] = { recs, chunk_key, key_sorted, chunk_fill, ctrs, chunk_id, chunk_sorted, cm, cs, om, os, totals, scan_tmp, cub_tmp,
+	void *tmp[] = { recs, chunk_key, key_sorted, chunk_fill, ctrs, chunk_id, chunk_sorted, cm, cs, om, os, totals, scan_tmp,
 	                stripe_done, lrecs, lprev };
 	for (void *q : tmp) c->release(q);
 	if (!sharded && (u64)tot[0] + tot[1] != n) { harcgpu_set_error("reorder lost reads: %u matched + %u singletons != %u", tot[0], tot[1], n); return -1; }
