@@ -1,14 +1,17 @@
-// Stable LSD radix sort of (u64 key, u32 value) pairs, 8 bits per pass -- the sort behind the dictionary build
-// (reorder.cpp:305 std::sort of the keys + the CSR fill of 344-391 in one go: sorting (key, read id) pairs stably leaves
-// the ids ascending inside a bin), the chunk order of stage I's finalize and the merge order of stage II.
+// Stable LSD radix sort of (u64 key, u32 value) pairs, 8 bits per pass, single sweep per pass ("onesweep") -- the sort
+// behind the dictionary build (reorder.cpp:305 std::sort of the keys + the CSR fill of 344-391 in one go: sorting
+// (key, read id) pairs stably leaves the ids ascending inside a bin), the chunk order of stage I's finalize and the
+// merge order of stage II.
 //
-// Per pass: rs_hist_kernel counts the digits of every tile of 4096 pairs into hist[digit][tile]; one exclusive scan over
-// that array (digit-major) is at once the global start of every digit and the offset of every tile inside it;
-// rs_scatter_kernel ranks the tile again (warp-level match of equal digits, item by item, so equal keys keep their
-// order), stages the tile in shared memory in digit order and writes every digit's run contiguously.  HBM traffic per
-// pass and pair: 8 B (histogram) + 12 B read + 12 B written.  The two buffers are used in turn; the caller gets told
-// which one holds the result.
+// rs_ghist_kernel reads the keys once and counts the digits of ALL passes; their scans are the global starts of every
+// digit.  A pass is then one kernel: a block takes the next tile of 4096 pairs (ticket), ranks it (warp-level match of
+// equal digits, item by item, so equal keys keep their order), publishes its digit counts and adds up the counts of the
+// tiles before it by decoupled look-back (a tile publishes first its own counts, then the inclusive prefix; a later
+// tile walks back until it meets an inclusive one), stages the tile in shared memory in digit order and writes every
+// digit's run contiguously.  HBM traffic per pass and pair: 12 B read + 12 B written, plus 8 B once for the histograms.
+// The two buffers are used in turn and swapped, so the caller finds the result in *keys / *vals.
 #include "ctx.h"
+#include <algorithm>
 #include <utility>
 
 namespace {
@@ -17,20 +20,49 @@ constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS; // 4096
 constexpr int RS_WARPS = RS_THREADS / 32;
 
-__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const u64 *__restrict__ keys, size_t n, int shift, u32 dmask, u32 tiles,
-                                                             u32 *__restrict__ hist)
+constexpr int RS_MAXPASS = 8;
+constexpr u64 RS_PARTIAL = 1ull << 62, RS_INCLUSIVE = 1ull << 63, RS_COUNT = RS_PARTIAL - 1;
+
+// digit counts of every pass: ghist[pass][digit]
+__global__ void __launch_bounds__(RS_THREADS) rs_ghist_kernel(const u64 *__restrict__ keys, size_t n, int begin_bit, int end_bit, int passes,
+                                                              u32 *__restrict__ ghist)
 {
-	__shared__ u32 cnt[256];
-	cnt[threadIdx.x] = 0;
+	__shared__ u32 cnt[RS_MAXPASS][256];
+	for (int k = threadIdx.x; k < RS_MAXPASS * 256; k += RS_THREADS) (&cnt[0][0])[k] = 0;
 	__syncthreads();
-	const size_t base = (size_t)blockIdx.x * RS_TILE;
+	for (size_t idx = (size_t)blockIdx.x * RS_THREADS + threadIdx.x; idx < n; idx += (size_t)gridDim.x * RS_THREADS) {
+		const u64 k = __ldg(&keys[idx]);
 #pragma unroll
-	for (int i = 0; i < RS_ITEMS; i++) {
-		const size_t idx = base + (size_t)i * RS_THREADS + threadIdx.x;
-		if (idx < n) atomicAdd(&cnt[(u32)(__ldg(&keys[idx]) >> shift) & dmask], 1u);
+		for (int p = 0; p < RS_MAXPASS; p++) {
+			if (p < passes) {
+				const int shift = begin_bit + 8 * p;
+				const u32 dmask = end_bit - shift >= 8 ? 255u : (1u << (end_bit - shift)) - 1u;
+				atomicAdd(&cnt[p][(u32)(k >> shift) & dmask], 1u);
+			}
+		}
 	}
 	__syncthreads();
-	hist[(size_t)threadIdx.x * tiles + blockIdx.x] = cnt[threadIdx.x];
+	for (int k = threadIdx.x; k < passes * 256; k += RS_THREADS) {
+		const u32 v = (&cnt[0][0])[k];
+		if (v) atomicAdd(&ghist[k], v);
+	}
+}
+// gstart[pass][digit] = exclusive scan of ghist[pass][*]
+__global__ void __launch_bounds__(256) rs_gscan_kernel(const u32 *__restrict__ ghist, u32 *__restrict__ gstart)
+{
+	__shared__ u32 wsum[8];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const u32 v = ghist[blockIdx.x * 256 + threadIdx.x];
+	u32 incl = v;
+	for (int o = 1; o < 32; o <<= 1) {
+		const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl += t;
+	}
+	if (lane == 31) wsum[w] = incl;
+	__syncthreads();
+	u32 before = incl - v;
+	for (int k = 0; k < w; k++) before += wsum[k];
+	gstart[blockIdx.x * 256 + threadIdx.x] = before;
 }
 
 struct RsSmem {
@@ -38,22 +70,25 @@ struct RsSmem {
 	u32 val[RS_TILE];
 	u32 wh[RS_WARPS][256]; // per warp: count, then start inside the tile's run of the digit
 	u32 dstart[256];       // start of the digit's run inside the tile
-	u32 gbase[256];        // global index of the first pair of the digit's run of this tile
-	u32 wsum[RS_WARPS];
+	u64 gbase[256];        // global index of the first pair of the digit's run of this tile
+	u32 wsum[8];
+	u32 ticket;
 };
 
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
                                                                 u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, size_t n, int shift,
-                                                                u32 dmask, u32 tiles, const u32 *__restrict__ offs)
+                                                                u32 dmask, const u32 *__restrict__ gstart, u64 *lookback, u32 *ticket_ctr)
 {
 	extern __shared__ uint4 rs_raw[];
 	RsSmem &s = *reinterpret_cast<RsSmem *>(rs_raw);
 	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-	const size_t tbase = (size_t)blockIdx.x * RS_TILE;
-	const u32 tile_n = (u32)min((size_t)RS_TILE, n - tbase);
+	// tiles are taken in ticket order, so every tile a block looks back at belongs to a block that already runs
+	if (tid == 0) s.ticket = atomicAdd(ticket_ctr, 1u);
 	for (int k = tid; k < RS_WARPS * 256; k += RS_THREADS) (&s.wh[0][0])[k] = 0;
-	s.gbase[tid] = offs[(size_t)tid * tiles + blockIdx.x];
 	__syncthreads();
+	const u32 tile = s.ticket;
+	const size_t tbase = (size_t)tile * RS_TILE;
+	const u32 tile_n = (u32)min((size_t)RS_TILE, n - tbase);
 	// warp-striped: warp w owns positions [512 w, 512 w + 512) of the tile, item i of lane l is position 512 w + 32 i + l,
 	// so (item, lane) order is position order
 	u64 key[RS_ITEMS];
@@ -62,8 +97,24 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__res
 #pragma unroll
 	for (int i = 0; i < RS_ITEMS; i++) {
 		const u32 p = (u32)w * (32 * RS_ITEMS) + 32 * i + lane;
+		key[i] = p < tile_n ? __ldg(&keys_in[tbase + p]) : 0ull;
+	}
+	// the tile's digit counts first (plain shared-memory atomics), published at once: the tiles behind this one can
+	// add them up while this one is still ranking
+	if (tid < 256) s.dstart[tid] = 0;
+	__syncthreads();
+#pragma unroll
+	for (int i = 0; i < RS_ITEMS; i++) {
+		const u32 p = (u32)w * (32 * RS_ITEMS) + 32 * i + lane;
+		if (p < tile_n) atomicAdd(&s.dstart[(u32)(key[i] >> shift) & dmask], 1u);
+	}
+	__syncthreads();
+	volatile u64 *lb = lookback;
+	if (tid < 256) lb[(size_t)tile * 256 + tid] = (u64)s.dstart[tid] | RS_PARTIAL;
+#pragma unroll
+	for (int i = 0; i < RS_ITEMS; i++) {
+		const u32 p = (u32)w * (32 * RS_ITEMS) + 32 * i + lane;
 		const bool valid = p < tile_n;
-		key[i] = valid ? __ldg(&keys_in[tbase + p]) : 0ull;
 		const u32 d = valid ? ((u32)(key[i] >> shift) & dmask) : (256u + lane); // pairs behind the end match nobody
 		const u32 peers = __match_any_sync(0xffffffffu, d);
 		const int leader = __ffs(peers) - 1;
@@ -73,20 +124,35 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__res
 		rank[i] = old + __popc(peers & lt);
 	}
 	__syncthreads();
-	// digit tid: starts of the warps' runs inside the digit's run, then the start of the digit's run inside the tile
-	u32 run = 0;
+	// digit tid (the first 256 threads): starts of the warps' runs inside the digit's run, look-back, then the start of
+	// the digit's run inside the tile
+	u32 run = 0, incl = 0;
+	if (tid < 256) {
 #pragma unroll
-	for (int k = 0; k < RS_WARPS; k++) { const u32 t = s.wh[k][tid]; s.wh[k][tid] = run; run += t; }
-	u32 incl = run;
-	for (int o = 1; o < 32; o <<= 1) {
-		const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
-		if (lane >= o) incl += t;
+		for (int k = 0; k < RS_WARPS; k++) { const u32 t = s.wh[k][tid]; s.wh[k][tid] = run; run += t; }
+		// decoupled look-back over the tiles before this one, for digit tid
+		u64 excl = 0;
+		for (long long t = (long long)tile - 1; t >= 0; t--) {
+			u64 v;
+			do { v = lb[(size_t)t * 256 + tid]; } while ((v & (RS_PARTIAL | RS_INCLUSIVE)) == 0);
+			excl += v & RS_COUNT;
+			if (v & RS_INCLUSIVE) break;
+		}
+		lb[(size_t)tile * 256 + tid] = (excl + run) | RS_INCLUSIVE;
+		s.gbase[tid] = (u64)gstart[tid] + excl;
+		incl = run;
+		for (int o = 1; o < 32; o <<= 1) {
+			const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		if (lane == 31) s.wsum[w] = incl;
 	}
-	if (lane == 31) s.wsum[w] = incl;
 	__syncthreads();
-	u32 before = incl - run;
-	for (int k = 0; k < w; k++) before += s.wsum[k];
-	s.dstart[tid] = before;
+	if (tid < 256) {
+		u32 before = incl - run;
+		for (int k = 0; k < w; k++) before += s.wsum[k];
+		s.dstart[tid] = before;
+	}
 	__syncthreads();
 #pragma unroll
 	for (int i = 0; i < RS_ITEMS; i++) {
@@ -102,7 +168,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__res
 	for (u32 q = tid; q < tile_n; q += RS_THREADS) {
 		const u64 k = s.key[q];
 		const u32 d = (u32)(k >> shift) & dmask;
-		const size_t dst = (size_t)s.gbase[d] + (q - s.dstart[d]);
+		const size_t dst = (size_t)(s.gbase[d] + (q - s.dstart[d]));
 		keys_out[dst] = k;
 		vals_out[dst] = s.val[q];
 	}
@@ -118,21 +184,28 @@ int radix_sort_pairs(harcgpu_ctx *c, u64 **keys, u64 **keys_alt, u32 **vals, u32
 	if (n >= 0xffffffffull) { harcgpu_set_error("radix sort: too many pairs"); return -1; }
 	cudaStream_t st = c->st;
 	const u32 tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
-	const size_t hn = (size_t)256 * tiles;
-	u32 *hist = nullptr, *offs = nullptr;
-	u64 *scan_tmp = nullptr;
-	if (c->alloc(&hist, hn) || c->alloc(&offs, hn) || c->alloc(&scan_tmp, scan_tmp_elems(hn))) return -1;
+	const int passes = (end_bit - begin_bit + 7) / 8;
+	if (passes > RS_MAXPASS) { harcgpu_set_error("radix sort: more than 64 key bits"); return -1; }
+	u32 *ghist = nullptr, *gstart = nullptr, *ticket = nullptr;
+	u64 *lookback = nullptr;
+	const size_t lbn = (size_t)passes * tiles * 256;
+	if (c->alloc(&ghist, passes * 256) || c->alloc(&gstart, passes * 256) || c->alloc(&ticket, passes) || c->alloc(&lookback, lbn)) return -1;
+	CK(cudaMemsetAsync(ghist, 0, sizeof(u32) * passes * 256, st));
+	CK(cudaMemsetAsync(ticket, 0, sizeof(u32) * passes, st));
+	CK(cudaMemsetAsync(lookback, 0, sizeof(u64) * lbn, st));
 	CK(cudaFuncSetAttribute(rs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
-	for (int shift = begin_bit; shift < end_bit; shift += 8) {
+	rs_ghist_kernel<<<KL + (unsigned)std::min<size_t>(tiles, 148 * 8), RS_THREADS, 0, st>>>(*keys, n, begin_bit, end_bit, passes, ghist);
+	rs_gscan_kernel<<<KL + passes, 256, 0, st>>>(ghist, gstart);
+	CK(cudaGetLastError());
+	for (int p = 0; p < passes; p++) {
+		const int shift = begin_bit + 8 * p;
 		const u32 dmask = end_bit - shift >= 8 ? 255u : (1u << (end_bit - shift)) - 1u; // only bits below end_bit count
-		rs_hist_kernel<<<KL + tiles, RS_THREADS, 0, st>>>(*keys, n, shift, dmask, tiles, hist);
-		CK(cudaGetLastError());
-		if (exclusive_scan_u32(hist, offs, hn, scan_tmp, nullptr, st)) return -1;
-		rs_scatter_kernel<<<KL + tiles, RS_THREADS, sizeof(RsSmem), st>>>(*keys, *vals, *keys_alt, *vals_alt, n, shift, dmask, tiles, offs);
+		rs_scatter_kernel<<<KL + tiles, RS_THREADS, sizeof(RsSmem), st>>>(*keys, *vals, *keys_alt, *vals_alt, n, shift, dmask, gstart + p * 256,
+		                                                                  lookback + (size_t)p * tiles * 256, ticket + p);
 		CK(cudaGetLastError());
 		std::swap(*keys, *keys_alt);
 		std::swap(*vals, *vals_alt);
 	}
-	c->release(hist); c->release(offs); c->release(scan_tmp);
+	c->release(ghist); c->release(gstart); c->release(ticket); c->release(lookback);
 	return 0;
 }

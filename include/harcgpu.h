@@ -75,7 +75,7 @@ int harcgpu_default_params(int readlen, harcgpu_params *p);
 int harcgpu_create(int device, const harcgpu_params *p, harcgpu_ctx **out);
 void harcgpu_destroy(harcgpu_ctx *ctx);
 const char *harcgpu_last_error(void);
-/* Number of kernels this library has launched in this process (its own kernels; CUB sort passes not counted). */
+/* Number of kernels this library has launched in this process (every kernel on the path is the library's own). */
 uint64_t harcgpu_launch_count(void);
 int harcgpu_device_count(void);
 
