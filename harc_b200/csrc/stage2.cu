@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(CONS_T) consensus_kernel(const u64 *__restrict
 			khi = lo;
 		}
 		u64 cnt = 0; // four 16-bit counters, bit-code order A G C T; a chunk adds at most CONS_R votes
+#pragma unroll 4
 		for (u32 k = klo; k < khi; k++) {
 			const u32 o = (u32)(tid - sG[k]);
 			if (o < (u32)L) {
@@ -304,6 +305,10 @@ __global__ void __launch_bounds__(PROBE_T) pool_probe_kernel(PoolArgs a)
 	if (g + L > __ldg(&a.G[next])) return;        // j <= ref.size()-readlen (encoder.cpp:252)
 	u64 w[NW], rc[NW];
 	bool have_w = false, have_rc = false;
+	// the four window keys and their Bloom words first, so that the four L2 round trips overlap
+	u64 k3s[4];
+	u32 bword[4], bbits[4];
+#pragma unroll
 	for (int q = 0; q < 4; q++) { // forward dict 0, forward dict 1, reverse dict 0, reverse dict 1 (encoder.cpp:270, 338)
 		const int l = q & 1;
 		const bool rev = q >= 2;
@@ -315,10 +320,18 @@ __global__ void __launch_bounds__(PROBE_T) pool_probe_kernel(PoolArgs a)
 			k2 = getbits_g(a.cons2, 2 * (g + L - 1 - dv.dend), 2 * nb);
 			k2 = revpairs64(~k2 & lowmask(2 * nb)) >> (64 - 2 * nb);
 		}
-		const u64 k3 = spread2to3(k2, nb);
-		u32 bw, bb;
-		bloom_pos(k3, l, a.bloom_mask, bw, bb);
-		if ((__ldg(&a.bloom[bw]) & bb) != bb) continue;
+		k3s[q] = spread2to3(k2, nb);
+		u32 bw;
+		bloom_pos(k3s[q], l, a.bloom_mask, bw, bbits[q]);
+		bword[q] = __ldg(&a.bloom[bw]);
+	}
+#pragma unroll
+	for (int q = 0; q < 4; q++) {
+		const int l = q & 1;
+		const bool rev = q >= 2;
+		const DictView &dv = a.d[l];
+		const u64 k3 = k3s[q];
+		if ((bword[q] & bbits[q]) != bbits[q]) continue;
 		u32 bstart, bsize;
 		if (!dict_lookup(dv, k3, bstart, bsize)) continue;
 		if (!have_w) { load_window<NW>(a.cons2, g, L, w); have_w = true; }
