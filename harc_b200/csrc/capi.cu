@@ -221,7 +221,7 @@ int harcgpu_build_dicts(harcgpu_ctx *c)
 		DictShard sh;
 		if (c->dicts_sharded) {
 			char *arena = (char *)c->seg[c->shard_rank];
-			sh.rank = c->shard_rank; sh.world = c->shard_world; sh.cap = c->shard_cap;
+			sh.rank = c->shard_rank; sh.world = c->shard_world; sh.cap = c->shard_cap; sh.nslots = c->shard_nslots;
 			sh.slots = (ulonglong2 *)(arena + c->arena_slots_off[l]);
 			sh.ids = (u32 *)(arena + c->arena_ids_off[l]);
 		}
@@ -242,12 +242,24 @@ int harcgpu_dump_dict(harcgpu_ctx *c, int stage, int l, uint64_t *keys, uint32_t
 	if (!d.ids) { harcgpu_set_error("dictionary not built"); return -1; }
 	if (numkeys) *numkeys = d.numkeys;
 	if (nids) *nids = n;
-	if (keys) CK(cudaMemcpy(keys, d.keys, 8 * (size_t)d.numkeys, cudaMemcpyDeviceToHost));
-	if (ids) CK(cudaMemcpy(ids, d.ids, 4 * (size_t)n, cudaMemcpyDeviceToHost));
-	if (counts) {
-		std::vector<u32> st((size_t)d.numkeys + 1);
-		CK(cudaMemcpy(st.data(), d.start, 4 * ((size_t)d.numkeys + 1), cudaMemcpyDeviceToHost));
-		for (u32 i = 0; i < d.numkeys; i++) counts[i] = st[i + 1] - st[i];
+	if (!keys && !ids && !counts) return 0;
+	// The dictionary lives in mixed-key order (common.cuh); the canonical view is by key: un-mix and sort on the host
+	// (a test hook, not on the hot path).
+	const size_t nk = d.numkeys;
+	std::vector<u64> mk(nk);
+	std::vector<u32> st(nk + 1), hid(n);
+	CK(cudaMemcpy(mk.data(), d.keys, 8 * nk, cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(st.data(), d.start, 4 * (nk + 1), cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(hid.data(), d.ids, 4 * (size_t)(nk ? st[nk] : 0), cudaMemcpyDeviceToHost));
+	std::vector<u32> perm(nk);
+	for (size_t i = 0; i < nk; i++) { perm[i] = (u32)i; mk[i] = key_unmix(mk[i]); }
+	std::sort(perm.begin(), perm.end(), [&](u32 x, u32 y) { return mk[x] < mk[y]; });
+	size_t w = 0;
+	for (size_t i = 0; i < nk; i++) {
+		const u32 b = perm[i];
+		if (keys) keys[i] = mk[b];
+		if (counts) counts[i] = st[b + 1] - st[b];
+		if (ids) for (u32 k = st[b]; k < st[b + 1]; k++) ids[w++] = hid[k];
 	}
 	return 0;
 }
@@ -295,8 +307,9 @@ int harcgpu_shard_init(harcgpu_ctx *c, int rank, int world, uint32_t n_total, vo
 		while (cap < 2 * per + per / 4 + 1024) cap <<= 1; // load factor <= 0.45 even for a shard 10 % above the mean
 		if (cap > 0x80000000ull) { harcgpu_set_error("dictionary shard too large"); return -1; }
 		c->shard_cap = (u32)cap;
+		c->shard_nslots = cap + cap / 8 + 1024;
 		for (int l = 0; l < c->p.numdict; l++) {
-			c->arena_slots_off[l] = off; off += (size_t)cap * sizeof(ulonglong2);
+			c->arena_slots_off[l] = off; off += (size_t)c->shard_nslots * sizeof(ulonglong2);
 			c->arena_ids_off[l] = off;   off += round256((size_t)n_total * 4); // worst case: every read in one shard
 		}
 		for (int l = 0; l < 2; l++) free_dict(c, c->d1[l]);

@@ -40,80 +40,79 @@ __device__ __forceinline__ u64 getbits(const u64 *w, int words, int pos, int n)
 // mask with the low `n` bits set, n clamped to [0,64]
 __device__ __forceinline__ u64 lowmask(int n) { return n >= 64 ? ~0ull : (n <= 0 ? 0ull : ((1ull << n) - 1)); }
 
-// Slot hash of the key-storing table that stands in for BooPHF (BooPHF.h:970-1008): one 64-bit multiply, the high
-// half (the well-mixed one) folded with the low half.
-__device__ __forceinline__ u32 slot_hash(u64 x)
-{
-	x *= 0x9E3779B97F4A7C15ull;
-	return (u32)(x >> 32) ^ (u32)x;
-}
-struct DictView;
+// ---- the key table that stands in for BooPHF (BooPHF.h:970-1008) ------------------------------------------------
+// A key is mixed by one 64-bit multiply (a bijection, so equal keys <=> equal mixed keys); the table is ORDERED by the
+// mixed key: the home bucket of a key is the top bits of its mixed value, and the bins are placed in mixed-key order
+// by linear probing -- which, for sorted input, is a prefix maximum (stage1.cu: place_kernel) instead of one atomic
+// per bin.  The mixed key is also what the slots store and what lookups compare.
+constexpr u64 KEY_MIX = 0x9E3779B97F4A7C15ull;   // 2^64 / golden ratio, odd
+constexpr u64 KEY_UNMIX = 0xF1DE83E19937733Dull; // its inverse modulo 2^64
+__device__ __host__ __forceinline__ u64 key_mix(u64 key) { return key * KEY_MIX; }
+__device__ __host__ __forceinline__ u64 key_unmix(u64 t) { return t * KEY_UNMIX; }
+// One job on several GPUs with sharded dictionaries: shard = floor(t * world / 2^64); inside a shard t * world (mod 2^64)
+// runs over the whole 64-bit range again, monotonically, and takes the place of t for the home bucket.
+__device__ __forceinline__ u32 mix_shard(u64 t, int world) { return (u32)__umul64hi(t, (u64)world); }
+// home bucket (even slot) of mixed key t in a table of 2^(64 - shift) nominal slots
+__device__ __forceinline__ u32 slot_home(u64 t, int shift, int world) { return (u32)((world > 1 ? t * (u64)world : t) >> shift) & ~1u; }
 
-// One dictionary: canonical CSR (keys ascending, ids ascending inside a bin: reorder.cpp:344-391) plus an
-// open-addressing table key -> bin.  A slot is 16 bytes {key, val}: val == 0 = empty, else size = bits 32..62 and the low
-// half is the bin's first index into ids[] -- or, for a bin of one read (most bins), the read id itself, so that the
-// common probe needs no second dependent load.
+// One dictionary: CSR over the bins in mixed-key order (ids ascending inside a bin: reorder.cpp:344-391) plus the
+// open-addressing table mixed key -> bin.  A slot is 16 bytes {mixed key, val}: val == 0 = empty, else size = bits 32..62
+// and the low half is the bin's first index into ids[] -- or, for a bin of one read (most bins), the read id itself, so
+// that the common probe needs no second dependent load.
 struct DictDev {
 	bool external = false;    // slots and ids live in the shard arena (one job on several GPUs): not owned
-	u64 *keys = nullptr;      // [numkeys] ascending
+	u64 *keys = nullptr;      // [numkeys] mixed keys, ascending
 	u32 *start = nullptr;     // [numkeys+1]
 	u32 *ids = nullptr;       // [n]
 	ulonglong2 *slots = nullptr;
 	u32 numkeys = 0;
-	u32 slot_mask = 0;
+	int slot_shift = 60;      // home bucket = (mixed key >> slot_shift) & ~1
+	u64 nslots = 0;           // allocated slots (nominal 2^(64 - slot_shift) + spill + 2 empty ones at the end)
 	int bitpos = 0, nbits = 0; // key = bits [bitpos, bitpos+nbits) of the packed read
 };
 struct DictView {
 	const ulonglong2 *slots;
 	const u32 *ids;
-	u32 slot_mask;
+	int slot_shift;
 	int dstart, dend; // in bases
-	// one job on several GPUs with sharded dictionaries: shard s of the table and of the id lists (peer memory), every
-	// shard with slot_mask + 1 slots; world == 0 otherwise
+	// one job on several GPUs with sharded dictionaries: shard s of the table and of the id lists (peer memory), all
+	// shards with the same slot_shift; world == 0 otherwise
 	const ulonglong2 *sslots[8];
 	const u32 *sids[8];
 	int world;
 };
-// 64-bit product behind slot_hash; the shard of a key comes from bits the slot index does not use
-__device__ __host__ __forceinline__ u64 key_mix(u64 x) { return x * 0x9E3779B97F4A7C15ull; }
-__device__ __host__ __forceinline__ u32 mix_slot(u64 m) { return (u32)(m >> 32) ^ (u32)m; }
-__device__ __host__ __forceinline__ u32 mix_shard(u64 m, int world) { return (u32)((((m >> 40) & 0xffffffull) * (u64)world) >> 24); }
 
-// Slots are probed in buckets of two (one 32-byte sector): a key hashes to an even slot (its home bucket) and is inserted
-// into the first empty slot from there on.  A key that did not fit into its home bucket sets the OVERFLOW bit (bit 63 of
-// val) of the home bucket's first slot, so a lookup that misses in the home bucket only goes on when that bit is set:
-// ~95 % of all lookups, present or absent, end after one 32-byte load.
+// Slots are probed in buckets of two (one 32-byte sector).  A bin that did not fit into its home bucket sets the
+// OVERFLOW bit (bit 63 of val) of the home bucket's first slot, so a lookup that misses in the home bucket only goes on
+// when that bit is set: ~95 % of all lookups, present or absent, end after one 32-byte load.  A lookup that goes on
+// walks towards higher slots until it meets an empty one; the table ends with two empty slots and never wraps.
 // val = overflow << 63 | size << 32 | lo; size == 0 <=> empty slot.
 constexpr u64 SLOT_OVERFLOW = 1ull << 63;
 __device__ __forceinline__ u32 slot_size(u64 val) { return (u32)(val >> 32) & 0x7fffffffu; }
 
-// One step of a lookup over the bucket (s0, s1); `home` = this is the key's home bucket.
+// One step of a lookup of mixed key t over the bucket (s0, s1); `home` = this is the key's home bucket.
 // returns 1: found (lo, size set), 0: absent, 2: go on with the next bucket
-__device__ __forceinline__ int bucket_step(u64 key, ulonglong2 s0, ulonglong2 s1, bool home, u32 &lo, u32 &size)
+__device__ __forceinline__ int bucket_step(u64 t, ulonglong2 s0, ulonglong2 s1, bool home, u32 &lo, u32 &size)
 {
 	const u32 z0 = slot_size(s0.y), z1 = slot_size(s1.y);
-	if (z0 != 0u && s0.x == key) { lo = (u32)s0.y; size = z0; return 1; }
-	if (z0 != 0u && z1 != 0u && s1.x == key) { lo = (u32)s1.y; size = z1; return 1; }
+	if (z0 != 0u && s0.x == t) { lo = (u32)s0.y; size = z0; return 1; }
+	if (z0 != 0u && z1 != 0u && s1.x == t) { lo = (u32)s1.y; size = z1; return 1; }
 	if (home) return (s0.y & SLOT_OVERFLOW) ? 2 : 0;
 	return (z0 != 0u && z1 != 0u) ? 2 : 0;
 }
 // true if the key is present: size = reads in the bin, lo = first index into ids[] (size > 1) or the read id (size == 1)
-__device__ __forceinline__ bool dict_resolve(const DictView &d, u64 key, u32 h, ulonglong2 s0, ulonglong2 s1, u32 &lo, u32 &size)
-{
-	bool home = true;
-	while (true) {
-		const int r = bucket_step(key, s0, s1, home, lo, size);
-		if (r != 2) return r == 1;
-		home = false;
-		h = (h + 2) & d.slot_mask;
-		s0 = __ldg(&d.slots[h]);
-		s1 = __ldg(&d.slots[h + 1]);
-	}
-}
+// (unsharded tables only: stage II)
 __device__ __forceinline__ bool dict_lookup(const DictView &d, u64 key, u32 &lo, u32 &size)
 {
-	const u32 h = slot_hash(key) & d.slot_mask & ~1u;
-	return dict_resolve(d, key, h, __ldg(&d.slots[h]), __ldg(&d.slots[h + 1]), lo, size);
+	const u64 t = key_mix(key);
+	u32 h = slot_home(t, d.slot_shift, 0);
+	bool home = true;
+	while (true) {
+		const int r = bucket_step(t, __ldg(&d.slots[h]), __ldg(&d.slots[h + 1]), home, lo, size);
+		if (r != 2) return r == 1;
+		home = false;
+		h += 2;
+	}
 }
 // entry t (0 = lowest id) of a bin returned by dict_lookup
 __device__ __forceinline__ u32 bin_entry(const DictView &d, u32 lo, u32 size, u32 t)

@@ -41,7 +41,8 @@ struct harcgpu_ctx {
 	// lists), so that one IPC handle per GPU is exchanged; seg[r] = bitmap range of GPU r = start of arena r.
 	u32 *seg[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // seg[shard_rank] is local
 	bool dicts_sharded = false;
-	u32 shard_cap = 0;                    // slots per dictionary shard (power of two)
+	u32 shard_cap = 0;                    // nominal slots per dictionary shard (power of two)
+	u64 shard_nslots = 0;                 // slots reserved per shard: nominal + room for the spill at the end
 	size_t arena_slots_off[2] = { 0, 0 }; // byte offsets inside an arena
 	size_t arena_ids_off[2] = { 0, 0 };
 	bool seg_opened[8] = { false, false, false, false, false, false, false, false };
@@ -177,7 +178,8 @@ int s1_packN(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *out2, u64 *outN);
 struct DictShard { // where a dictionary shard of one job on several GPUs is built (inside the arena of ctx.h)
 	int rank, world;
 	ulonglong2 *slots;
-	u32 cap;   // slots, power of two
+	u32 cap;   // nominal slots, power of two (fixes the home buckets)
+	u64 nslots; // slots the arena has room for: cap + spill
 	u32 *ids;  // room for every read id
 };
 int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, u32 n, int words, int ds, int de, int bits,

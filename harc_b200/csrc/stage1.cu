@@ -10,6 +10,8 @@
 // 16-byte-slot open-addressing table at load factor <= 0.5; a claim bitmap (1 bit/read); a chunked record log.
 #include "ctx.h"
 #include <utility>
+#include <algorithm>
+#include <limits.h>
 
 // ------------------------------------------------------------------------------------------------ K1 pack
 namespace {
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(256) keys_kernel(const u64 *__restrict__ reads
 	u64 v = __ldg(&r[q]) >> sh;
 	if (sh && q + 1 < words) v |= __ldg(&r[q + 1]) << (64 - sh);
 	if (nbits < 64) v &= (1ull << nbits) - 1;
-	keys[i] = v;
+	keys[i] = key_mix(v); // the dictionary is built, stored and probed in mixed-key order (common.cuh)
 	ids[i] = i;
 }
 
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(256) keys3_kernel(const u64 *__restrict__ r2, 
 		u64 nf = (__ldg(&rN[(size_t)i * words + (b >> 5)]) >> (2 * (b & 31))) & 1ull;
 		key |= ((c2 << 1) | nf) << (3 * (b - ds));
 	}
-	keys[i] = key;
+	keys[i] = key_mix(key);
 	ids[i] = i;
 }
 
@@ -148,28 +150,95 @@ __global__ void __launch_bounds__(256) bins_kernel(const u64 *__restrict__ ks, c
 	start[b] = i;
 }
 
-// One thread per bin: linear probing, CAS on the val half of the slot; the table is read-only afterwards.  A bin that lands
-// outside its home bucket raises the home bucket's overflow bit (common.cuh: bucket_step).
-__global__ void __launch_bounds__(256) insert_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ start, const u32 *__restrict__ ids,
-                                                     u32 numkeys, ulonglong2 *slots, u32 mask)
+// ---- placement of the bins in the key table.  The bins come in mixed-key order, so their home buckets never decrease
+// and sequential linear probing puts bin b at pos_b = max(home_b, pos_{b-1} + 1) = b + max_{j <= b}(home_j - j): an
+// inclusive prefix maximum instead of one atomic compare-and-swap per bin, and the slots are written in order.
+constexpr int PM_TILE = 1024; // bins per block of the prefix maximum: 256 threads x 4
+__global__ void __launch_bounds__(256) pm_local_kernel(const u64 *__restrict__ mixed, u32 nk, int shift, int world, long long *__restrict__ pm,
+                                                       long long *__restrict__ block_max)
 {
-	u32 b = blockIdx.x * blockDim.x + threadIdx.x;
-	if (b >= numkeys) return;
-	u64 key = keys[b];
-	u32 s = start[b], sz = start[b + 1] - s;
-	u64 val = (u64)(sz == 1 ? ids[s] : s) | ((u64)sz << 32);
-	const u32 h0 = slot_hash(key) & mask & ~1u; // buckets of two slots
-	u32 h = h0;
-	while (true) {
-		u64 old = atomicCAS(&slots[h].y, 0ull, val);
-		if (old == 0ull) {
-			slots[h].x = key;
-			// the home bucket was full (both CAS failed on non-zero words), so the bit never lands on an empty slot
-			if ((h & ~1u) != h0) atomicOr(&slots[h0].y, SLOT_OVERFLOW);
-			return;
-		}
-		h = (h + 1) & mask;
+	__shared__ long long wmax[8];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const size_t b0 = (size_t)blockIdx.x * PM_TILE + 4 * threadIdx.x;
+	long long v[4], run = LLONG_MIN;
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const size_t b = b0 + k;
+		v[k] = b < nk ? (long long)slot_home(mixed[b], shift, world) - (long long)b : LLONG_MIN;
+		run = max(run, v[k]);
+		v[k] = run; // inclusive inside the thread
 	}
+	long long incl = run;
+	for (int o = 1; o < 32; o <<= 1) {
+		const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl = max(incl, t);
+	}
+	if (lane == 31) wmax[w] = incl;
+	__syncthreads();
+	long long before = __shfl_up_sync(0xffffffffu, incl, 1);
+	if (lane == 0) before = LLONG_MIN;
+	for (int k = 0; k < w; k++) before = max(before, wmax[k]);
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+		if (b0 + k < nk) pm[b0 + k] = max(v[k], before);
+	if (threadIdx.x == 255) block_max[blockIdx.x] = max(incl, before);
+}
+// exclusive prefix maximum of the block maxima, by one block
+__global__ void __launch_bounds__(1024) pm_blocks_kernel(long long *block_max, u32 nblocks)
+{
+	__shared__ long long wmax[32];
+	__shared__ long long carry_s;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	if (threadIdx.x == 0) carry_s = LLONG_MIN;
+	__syncthreads();
+	for (u32 base = 0; base < nblocks; base += 1024) {
+		const u32 i = base + threadIdx.x;
+		const long long v = i < nblocks ? block_max[i] : LLONG_MIN;
+		long long incl = v;
+		for (int o = 1; o < 32; o <<= 1) {
+			const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl = max(incl, t);
+		}
+		if (lane == 31) wmax[w] = incl;
+		__syncthreads();
+		long long before = __shfl_up_sync(0xffffffffu, incl, 1);
+		if (lane == 0) before = LLONG_MIN;
+		for (int k = 0; k < w; k++) before = max(before, wmax[k]);
+		const long long carry = carry_s;
+		before = max(before, carry);
+		if (i < nblocks) block_max[i] = before; // exclusive
+		__syncthreads();
+		if (threadIdx.x == 1023) carry_s = max(before, v);
+		__syncthreads();
+	}
+}
+// slot of bin b = b + prefix maximum; last[0] = slot of the last bin (the table must reach two slots beyond it)
+__global__ void __launch_bounds__(256) pm_finish_kernel(long long *__restrict__ pm, const long long *__restrict__ block_excl, u32 nk, u32 *__restrict__ pos,
+                                                        unsigned long long *__restrict__ last)
+{
+	const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nk) return;
+	const long long m = max(pm[b], block_excl[b / PM_TILE]);
+	const long long p = (long long)b + m;
+	pos[b] = (u32)p;
+	if (b == nk - 1) last[0] = (unsigned long long)p;
+}
+__global__ void __launch_bounds__(256) place_kernel(const u64 *__restrict__ mixed, const u32 *__restrict__ start, const u32 *__restrict__ ids,
+                                                    const u32 *__restrict__ pos, u32 nk, ulonglong2 *__restrict__ slots)
+{
+	const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nk) return;
+	const u32 s = start[b], sz = start[b + 1] - s;
+	slots[pos[b]] = make_ulonglong2(mixed[b], (u64)(sz == 1 ? ids[s] : s) | ((u64)sz << 32));
+}
+// a bin outside its home bucket raises the home bucket's overflow bit (common.cuh: bucket_step); runs after place_kernel
+__global__ void __launch_bounds__(256) overflow_kernel(const u64 *__restrict__ mixed, const u32 *__restrict__ pos, u32 nk, int shift, int world,
+                                                       ulonglong2 *slots)
+{
+	const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nk) return;
+	const u32 h = slot_home(mixed[b], shift, world);
+	if (pos[b] > h + 1) atomicOr(&slots[h].y, SLOT_OVERFLOW);
 }
 } // namespace
 
@@ -213,7 +282,7 @@ namespace {
 __global__ void __launch_bounds__(256) shard_flag_kernel(const u64 *__restrict__ keys, u32 n, int rank, int world, u32 *__restrict__ flag)
 {
 	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) flag[i] = mix_shard(key_mix(keys[i]), world) == (u32)rank ? 1u : 0u;
+	if (i < n) flag[i] = mix_shard(keys[i], world) == (u32)rank ? 1u : 0u;
 }
 __global__ void __launch_bounds__(256) shard_compact_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ ids, const u32 *__restrict__ flag,
                                                             const u32 *__restrict__ ex, u32 n, u64 *__restrict__ k_out, u32 *__restrict__ id_out)
@@ -235,7 +304,6 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 		d.external = true;
 		d.ids = shard->ids;
 		d.slots = shard->slots;
-		d.slot_mask = shard->cap - 1;
 	}
 	const int bitpos = bits * ds, nbits = bits * (de - ds + 1);
 	d.bitpos = bitpos; d.nbits = nbits;
@@ -247,10 +315,19 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 		d.numkeys = 0;
 		if (c->alloc(&d.keys, 1) || c->alloc(&d.start, 1)) return -1;
 		CK(cudaMemsetAsync(d.start, 0, 4, st));
-		if (shard) { CK(cudaMemsetAsync(d.slots, 0, (size_t)shard->cap * sizeof(ulonglong2), st)); CK(cudaStreamSynchronize(st)); return 0; }
-		d.slot_mask = 15;
-		if (c->alloc(&d.slots, 16)) return -1;
-		CK(cudaMemsetAsync(d.slots, 0, 16 * sizeof(ulonglong2), st));
+		d.slot_shift = 60;
+		if (shard) {
+			int kb = 0;
+			while ((1ull << kb) < shard->cap) kb++;
+			d.slot_shift = 64 - kb;
+			d.nslots = shard->nslots;
+			CK(cudaMemsetAsync(d.slots, 0, (size_t)shard->nslots * sizeof(ulonglong2), st));
+			CK(cudaStreamSynchronize(st));
+			return 0;
+		}
+		d.nslots = 18;
+		if (c->alloc(&d.slots, 18)) return -1;
+		CK(cudaMemsetAsync(d.slots, 0, 18 * sizeof(ulonglong2), st));
 		return 0;
 	}
 	if (c->alloc(&k_in, n) || c->alloc(&k_out, n) || c->alloc(&id_in, n) || c->alloc(&head, n) || c->alloc(&binidx, n) ||
@@ -265,7 +342,7 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 		u64 *k_f = k_out;
 		u32 *id_f = nullptr;
 		if (c->alloc(&id_f, n)) return -1;
-		shard_flag_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(k_in, n, shard->rank, shard->world, flag);
+		shard_flag_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(k_in, n, shard->rank, shard->world, flag); // k_in holds mixed keys
 		CK(cudaGetLastError());
 		if (exclusive_scan_u32(flag, ex, n, scan_tmp, d_total, st)) return -1;
 		shard_compact_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(k_in, id_in, flag, ex, n, k_f, id_f);
@@ -281,7 +358,11 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 			d.numkeys = 0;
 			if (c->alloc(&d.keys, 1) || c->alloc(&d.start, 1)) return -1;
 			CK(cudaMemsetAsync(d.start, 0, 4, st));
-			CK(cudaMemsetAsync(d.slots, 0, (size_t)shard->cap * sizeof(ulonglong2), st));
+			int kb = 0;
+			while ((1ull << kb) < shard->cap) kb++;
+			d.slot_shift = 64 - kb;
+			d.nslots = shard->nslots;
+			CK(cudaMemsetAsync(d.slots, 0, (size_t)shard->nslots * sizeof(ulonglong2), st));
 			CK(cudaStreamSynchronize(st));
 			c->release(k_in); c->release(k_out); c->release(id_in); c->release(head); c->release(binidx);
 			c->release(scan_tmp); c->release(d_total);
@@ -290,7 +371,7 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 	}
 	// LSD radix sort is stable and ids start ascending, so ids stay ascending inside a bin (reorder.cpp:371-384)
 	if (c->alloc(&id_alt, n)) return -1;
-	if (radix_sort_pairs(c, &k_in, &k_out, &id_in, &id_alt, n, 0, nbits)) return -1;
+	if (radix_sort_pairs(c, &k_in, &k_out, &id_in, &id_alt, n, 0, 64)) return -1; // mixed keys use all 64 bits
 	std::swap(k_in, k_out); // k_out = sorted keys from here on
 	if (shard) CK(cudaMemcpyAsync(d.ids, id_in, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st)); // into the arena the peers have mapped
 	else { d.ids = id_in; id_in = nullptr; }
@@ -304,19 +385,44 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 	if (c->alloc(&d.keys, nk) || c->alloc(&d.start, (size_t)nk + 1)) return -1;
 	bins_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(k_out, head, binidx, n, nk, d.keys, d.start);
 	CK(cudaGetLastError());
+	// table: nominal 2^k >= 2 numkeys slots (k fixes the home buckets), placed in mixed-key order
 	u64 cap = 16;
+	int kbits = 4;
 	if (shard) {
 		cap = shard->cap;
+		kbits = 0;
+		while ((1ull << kbits) < cap) kbits++;
 		if ((u64)nk * 10 > cap * 9) { harcgpu_set_error("dictionary shard overflow: %u keys for %llu slots", nk, cap); return -1; }
 	} else {
-		while (cap < 2ull * nk) cap <<= 1;
-		d.slot_mask = (u32)(cap - 1);
-		if (c->alloc(&d.slots, cap)) return -1;
+		while (cap < 2ull * nk) { cap <<= 1; kbits++; }
 	}
-	CK(cudaMemsetAsync(d.slots, 0, cap * sizeof(ulonglong2), st));
-	insert_kernel<<<KL + cdiv(nk, 256), 256, 0, st>>>(d.keys, d.start, d.ids, nk, d.slots, d.slot_mask);
+	d.slot_shift = 64 - kbits;
+	const int world = shard ? shard->world : 0;
+	long long *pm = nullptr, *bmax = nullptr;
+	u32 *pos = nullptr;
+	unsigned long long *d_last = nullptr, h_last = 0;
+	const u32 pmb = cdiv(nk, PM_TILE);
+	if (c->alloc(&pm, nk) || c->alloc(&bmax, pmb) || c->alloc(&pos, nk) || c->alloc(&d_last, 1)) return -1;
+	pm_local_kernel<<<KL + pmb, 256, 0, st>>>(d.keys, nk, d.slot_shift, world, pm, bmax);
+	pm_blocks_kernel<<<KL + 1, 1024, 0, st>>>(bmax, pmb);
+	pm_finish_kernel<<<KL + cdiv(nk, 256), 256, 0, st>>>(pm, bmax, nk, pos, d_last);
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(&h_last, d_last, 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	const u64 need = std::max<u64>(cap, h_last + 1) + 2; // two empty slots end every probe sequence
+	if (shard) {
+		if (need > shard->nslots) { harcgpu_set_error("dictionary shard overflow: the table needs %llu slots, the arena has %llu", need, shard->nslots); return -1; }
+		d.nslots = shard->nslots;
+	} else {
+		d.nslots = need;
+		if (c->alloc(&d.slots, need)) return -1;
+	}
+	CK(cudaMemsetAsync(d.slots, 0, d.nslots * sizeof(ulonglong2), st));
+	place_kernel<<<KL + cdiv(nk, 256), 256, 0, st>>>(d.keys, d.start, d.ids, pos, nk, d.slots);
+	overflow_kernel<<<KL + cdiv(nk, 256), 256, 0, st>>>(d.keys, pos, nk, d.slot_shift, world, d.slots);
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(st));
+	c->release(pm); c->release(bmax); c->release(pos); c->release(d_last);
 	c->release(k_in); c->release(k_out); c->release(id_in); c->release(head); c->release(binidx);
 	c->release(scan_tmp); c->release(d_total); c->release(id_alt);
 	return 0;

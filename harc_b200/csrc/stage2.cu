@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) bloom_insert_kernel(const u64 *__restrict
 	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= nk) return;
 	u32 w, b;
-	bloom_pos(keys[i], l, mask, w, b);
+	bloom_pos(key_unmix(keys[i]), l, mask, w, b); // the dictionary stores mixed keys (common.cuh)
 	atomicOr(&bloom[w], b);
 }
 
@@ -860,7 +860,7 @@ int s2_encode(harcgpu_ctx *c)
 		a.G = G; a.cid = cid; a.cstart = cstart; a.m = m; a.NC = NC; a.per = per; a.TOT = TOT; a.cons2 = cons2;
 		a.pool = c->pool; a.poolN = c->poolN;
 		for (int l = 0; l < 2; l++) {
-			a.d[l].slots = c->d2[l].slots; a.d[l].ids = c->d2[l].ids; a.d[l].slot_mask = c->d2[l].slot_mask;
+			a.d[l].slots = c->d2[l].slots; a.d[l].ids = c->d2[l].ids; a.d[l].slot_shift = c->d2[l].slot_shift;
 			a.d[l].dstart = c->d2[l].bitpos / 3; a.d[l].dend = a.d[l].dstart + c->d2[l].nbits / 3 - 1;
 			a.d[l].world = 0;
 		}

@@ -361,14 +361,14 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? 8 : 4) walk_kernel(
 		const u32 w0 = w[0], w1 = w[1], w2 = w[2];
 		u32 klo = __funnelshift_r(w0, w1, r), khi = __funnelshift_r(w1, w2, r);
 		if (!full64) { klo &= lowmask32(kb); khi &= lowmask32(kb - 32); }
-		key = ((u64)khi << 32) | klo;
-		h = slot_hash(key) & dv.slot_mask & ~1u;
+		key = key_mix(((u64)khi << 32) | klo); // from here on the mixed key stands for the key (common.cuh)
+		h = slot_home(key, dv.slot_shift, dv.world);
 	};
 	// sharded dictionaries (one job on several GPUs): table and id lists of the shard that owns the key, in the owner's
 	// HBM and read over NVLink; dv.world == 0 (warp-uniform) otherwise
 	// (the per-shard pointers are indexed in the kernel parameters, not in a local copy)
-	auto slots_of = [&](u64 key) -> const ulonglong2 * { return dv.world ? a.d[l].sslots[mix_shard(key_mix(key), dv.world)] : dv.slots; };
-	auto ids_of = [&](u64 key) -> const u32 * { return dv.world ? a.d[l].sids[mix_shard(key_mix(key), dv.world)] : dv.ids; };
+	auto slots_of = [&](u64 t) -> const ulonglong2 * { return dv.world ? a.d[l].sslots[mix_shard(t, dv.world)] : dv.slots; };
+	auto ids_of = [&](u64 t) -> const u32 * { return dv.world ? a.d[l].sids[mix_shard(t, dv.world)] : dv.ids; };
 	auto issue = [&](int j, Probe &p) {
 		p.pend = (vmask >> (j >> SPR_LOG)) & 1u;
 		p.home = true;
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? 8 : 4) walk_kernel(
 					else if (r == 0) ps = P_DEAD;
 					else {
 						pc.home = false;
-						pc.h = (pc.h + 2) & dv.slot_mask;
+						pc.h += 2; // the table ends with two empty slots and never wraps
 						const ulonglong2 *sl = slots_of(pc.key);
 						pc.s0 = __ldg(&sl[pc.h]);
 						pc.s1 = __ldg(&sl[pc.h + 1]);
@@ -836,7 +836,7 @@ int s1_reorder(harcgpu_ctx *c)
 	a.numdict = c->p.numdict; a.extend = extend;
 	for (int l = 0; l < 2; l++) {
 		int ll = l < c->p.numdict ? l : 0;
-		a.d[l].slots = c->d1[ll].slots; a.d[l].ids = c->d1[ll].ids; a.d[l].slot_mask = c->d1[ll].slot_mask;
+		a.d[l].slots = c->d1[ll].slots; a.d[l].ids = c->d1[ll].ids; a.d[l].slot_shift = c->d1[ll].slot_shift;
 		a.d[l].dstart = c->p.dict_start[ll]; a.d[l].dend = c->p.dict_end[ll];
 		a.d[l].world = c->dicts_sharded ? c->shard_world : 0;
 		for (int r = 0; r < 8; r++) {
