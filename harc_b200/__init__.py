@@ -21,7 +21,7 @@ EXPORTS = [
     "harcgpu_load_pool_device", "harcgpu_launch_count", "harcgpu_stage_nreads",
     "harcgpu_shard_init", "harcgpu_shard_connect", "harcgpu_shard_reset", "harcgpu_set_pool_exchange", "harcgpu_load_pool_ids",
     "harcgpu_get_packed_order",
-    "harcgpu_fastq_readlen", "harcgpu_ingest_fastq", "harcgpu_ingest_fastq_device", "harcgpu_get_ingest", "harcgpu_load_pool_ingested",
+    "harcgpu_debug_sort", "harcgpu_fastq_readlen", "harcgpu_ingest_fastq", "harcgpu_ingest_fastq_device", "harcgpu_get_ingest", "harcgpu_load_pool_ingested",
 ]
 
 
@@ -98,6 +98,7 @@ def load_library():
     lib.harcgpu_load_pool_ids.argtypes = [vp, vp, u32, vp, u32]
     lib.harcgpu_get_packed_order.argtypes = [vp, vp, vp, vp, vp]
     lib.harcgpu_launch_count.restype = ctypes.c_uint64
+    lib.harcgpu_debug_sort.argtypes = [vp, vp, vp, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.harcgpu_fastq_readlen.argtypes = [vp, ctypes.c_uint64]
     lib.harcgpu_ingest_fastq.argtypes = [vp, vp, ctypes.c_uint64, ctypes.POINTER(IngestInfo)]
     lib.harcgpu_ingest_fastq_device.argtypes = [vp, vp, ctypes.c_uint64, ctypes.POINTER(IngestInfo)]
@@ -207,6 +208,13 @@ class HarcGpu:
 
     def load_pool_ingested(self):
         self._ck(self.lib.harcgpu_load_pool_ingested(self.h))
+
+    def debug_sort(self, keys, vals, mode=0, begin_bit=0, end_bit=64):
+        """Test hook: stable radix sort of (uint64 key, uint32 value) pairs; returns sorted copies."""
+        k = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+        v = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+        self._ck(self.lib.harcgpu_debug_sort(self.h, _ptr(k), _ptr(v), k.size, mode, begin_bit, end_bit))
+        return k, v
 
     # ---- stage I
     def load_reads(self, ascii_lines, n=None):

@@ -264,6 +264,27 @@ int harcgpu_dump_dict(harcgpu_ctx *c, int stage, int l, uint64_t *keys, uint32_t
 	return 0;
 }
 
+int harcgpu_debug_sort(harcgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t n, int mode, int begin_bit, int end_bit)
+{
+	if (!c || ((!keys || !vals) && n)) { harcgpu_set_error("null argument"); return -1; }
+	CK(cudaSetDevice(c->device));
+	u64 *k = nullptr, *k2 = nullptr;
+	u32 *v = nullptr, *v2 = nullptr;
+	if (c->alloc(&k, n) || c->alloc(&k2, n) || c->alloc(&v, n) || c->alloc(&v2, n)) return -1;
+	CK(cudaMemcpyAsync(k, keys, 8 * n, cudaMemcpyHostToDevice, c->st));
+	CK(cudaMemcpyAsync(v, vals, 4 * n, cudaMemcpyHostToDevice, c->st));
+	int rc = mode == 1 ? radix_sort_mixed(c, (u64 **)&k, (u64 **)&k2, &v, &v2, n)
+	       : mode == 2 ? radix_sort_pairs(c, (u64 **)&k, (u64 **)&k2, &v, &v2, n, begin_bit, end_bit)
+	                   : radix_sort_pairs(c, (u64 **)&k, (u64 **)&k2, &v, &v2, n, 0, 64);
+	if (!rc) {
+		CK(cudaMemcpyAsync(keys, k, 8 * n, cudaMemcpyDeviceToHost, c->st));
+		CK(cudaMemcpyAsync(vals, v, 4 * n, cudaMemcpyDeviceToHost, c->st));
+		CK(cudaStreamSynchronize(c->st));
+	}
+	c->release(k); c->release(k2); c->release(v); c->release(v2);
+	return rc;
+}
+
 int harcgpu_reorder(harcgpu_ctx *c)
 {
 	if (!c || !c->reads) { harcgpu_set_error("load reads first"); return -1; }

@@ -167,6 +167,7 @@ struct harcgpu_ctx {
 
 // sort.cu
 int radix_sort_pairs(harcgpu_ctx *c, u64 **keys, u64 **keys_alt, u32 **vals, u32 **vals_alt, size_t n, int begin_bit, int end_bit);
+int radix_sort_mixed(harcgpu_ctx *c, u64 **keys, u64 **keys_alt, u32 **vals, u32 **vals_alt, size_t n, bool force_full = false);
 // ingest.cu
 int ing_ingest(harcgpu_ctx *c, const char *d_fastq, u64 nbytes, u64 *total_reads, u32 *n_clean, u32 *n_N);
 int ing_unpack_clean(harcgpu_ctx *c, char *d_out);

@@ -173,6 +173,41 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__res
 		vals_out[dst] = s.val[q];
 	}
 }
+// ---- full 64-bit order from a sort by the top 32 bits.  Mixed keys (common.cuh) are spread over all 64 bits, so after a
+// stable sort by bits 32..63 a run of DIFFERENT keys that share their top half is a birthday collision: a few elements
+// long, and rare (n^2 / 2^33 pairs).  One thread per run head puts such a run in order of the low half with a stable
+// insertion sort; equal keys (the bins of a dictionary) are left as they are.  A run longer than RUN_MAX is reported and
+// the caller falls back to the full sort.
+constexpr int RUN_MAX = 32;
+__global__ void __launch_bounds__(256) runfix_kernel(u64 *__restrict__ keys, u32 *__restrict__ vals, size_t n, u32 *__restrict__ too_long)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const u64 k0 = keys[i];
+	if (i > 0 && (keys[i - 1] >> 32) == (k0 >> 32)) return; // not the head of a run
+	if (i + 1 >= n || (keys[i + 1] >> 32) != (k0 >> 32)) return; // run of one
+	u64 k[RUN_MAX];
+	u32 v[RUN_MAX];
+	int len = 0;
+	bool sorted = true;
+	while (i + len < n && (keys[i + len] >> 32) == (k0 >> 32)) {
+		if (len == RUN_MAX) { atomicMax(too_long, 1u); return; }
+		k[len] = keys[i + len];
+		v[len] = vals[i + len];
+		if (len && k[len] < k[len - 1]) sorted = false;
+		len++;
+	}
+	if (sorted) return; // e.g. one bin of equal keys
+	for (int a = 1; a < len; a++) { // stable insertion sort by the whole key
+		const u64 ka = k[a];
+		const u32 va = v[a];
+		int b = a - 1;
+		while (b >= 0 && k[b] > ka) { k[b + 1] = k[b]; v[b + 1] = v[b]; b--; }
+		k[b + 1] = ka;
+		v[b + 1] = va;
+	}
+	for (int a = 0; a < len; a++) { keys[i + a] = k[a]; vals[i + a] = v[a]; }
+}
 } // namespace
 
 // Sorts the n pairs (*keys, *vals) by the key bits [begin_bit, end_bit), stably.  *keys / *vals and *keys_alt / *vals_alt
@@ -208,4 +243,27 @@ int radix_sort_pairs(harcgpu_ctx *c, u64 **keys, u64 **keys_alt, u32 **vals, u32
 	}
 	c->release(ghist); c->release(gstart); c->release(ticket); c->release(lookback);
 	return 0;
+}
+
+// Stable sort by all 64 key bits for keys that are spread over the whole 64-bit range (mixed keys): four passes over the
+// top half, then the run fix-up; the full eight passes only if a run of different keys with one top half is longer than
+// RUN_MAX (not expected: it would be a 33-fold birthday collision in 2^32).  force_full (test hook) takes the slow path.
+int radix_sort_mixed(harcgpu_ctx *c, u64 **keys, u64 **keys_alt, u32 **vals, u32 **vals_alt, size_t n, bool force_full)
+{
+	if (n == 0) return 0;
+	cudaStream_t st = c->st;
+	if (!force_full) {
+		u32 *flag = nullptr, h = 0;
+		if (c->alloc(&flag, 1)) return -1;
+		CK(cudaMemsetAsync(flag, 0, 4, st));
+		if (radix_sort_pairs(c, keys, keys_alt, vals, vals_alt, n, 32, 64)) return -1;
+		runfix_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(*keys, *vals, n, flag);
+		CK(cudaGetLastError());
+		CK(cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		c->release(flag);
+		if (!h) return 0;
+	}
+	// every step so far was stable, so the full sort can start from whatever order the pairs are in now
+	return radix_sort_pairs(c, keys, keys_alt, vals, vals_alt, n, 0, 64);
 }

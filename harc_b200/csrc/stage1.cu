@@ -371,7 +371,7 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 	}
 	// LSD radix sort is stable and ids start ascending, so ids stay ascending inside a bin (reorder.cpp:371-384)
 	if (c->alloc(&id_alt, n)) return -1;
-	if (radix_sort_pairs(c, &k_in, &k_out, &id_in, &id_alt, n, 0, 64)) return -1; // mixed keys use all 64 bits
+	if (radix_sort_mixed(c, &k_in, &k_out, &id_in, &id_alt, n)) return -1; // mixed keys use all 64 bits
 	std::swap(k_in, k_out); // k_out = sorted keys from here on
 	if (shard) CK(cudaMemcpyAsync(d.ids, id_in, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st)); // into the arena the peers have mapped
 	else { d.ids = id_in; id_in = nullptr; }

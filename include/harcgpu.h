@@ -114,6 +114,10 @@ int harcgpu_build_dicts(harcgpu_ctx *ctx);
  * With NULL buffers only *numkeys and *nids are written. */
 int harcgpu_dump_dict(harcgpu_ctx *ctx, int stage, int l, uint64_t *keys, uint32_t *counts, uint32_t *ids,
                       uint32_t *numkeys, uint32_t *nids);
+/* Test hook: the library's stable radix sort of (u64 key, u32 value) pairs on host arrays, in place.  mode 0: all 64
+ * key bits, eight passes; 1: the dictionary build's route (four passes over the top half + fix-up of the runs that share
+ * it, full sort only if a run is too long); 2: bits [begin_bit, end_bit) only. */
+int harcgpu_debug_sort(harcgpu_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t n, int mode, int begin_bit, int end_bit);
 /* reorder.cpp:434-703 reorder() incl. 863-915 updaterefcount. */
 int harcgpu_reorder(harcgpu_ctx *ctx);
 int harcgpu_reorder_counts(harcgpu_ctx *ctx, uint32_t *n_matched, uint32_t *n_singleton, uint32_t *n_unmatched);
