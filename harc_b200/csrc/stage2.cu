@@ -17,6 +17,7 @@
 // scanned over its top 1000 ids only, without tracking removals; the result is still lossless.
 #include "ctx.h"
 #include <string.h>
+#include <stdlib.h>
 #include <utility>
 
 namespace {
@@ -224,6 +225,120 @@ __global__ void __launch_bounds__(CONS_T) consensus_kernel(const u64 *__restrict
 		v = lo | (hi << 1);
 		cons2[g >> 5] = v;
 	}
+}
+
+// The same vote, bit-sliced: one THREAD owns 16 consecutive columns (one u32 of the packed consensus).  A read that
+// touches them contributes a 32-bit window of its packed bases (one funnel shift), which is split into four one-hot
+// masks (one per base code, on the even bit positions); the masks are added to bit-sliced counters -- three low planes
+// per base, flushed every seven reads into twelve planes -- so a read costs ~80 instructions for 16 columns instead of
+// ~14 per column.  The argmax with ties A < C < G < T is a bit-sliced comparison.  Columns with more than 4000 covering
+// reads raise `deep`; the caller then runs consensus_kernel (exact for any depth) instead.
+constexpr int CS_THREADS = 128;
+constexpr int CS_COLS = 16;
+constexpr int CS_BLOCK_COLS = CS_THREADS * CS_COLS; // 2048
+constexpr int CS_SG = 4096;   // staged read starts per block
+constexpr int CS_PLANES = 12;
+__global__ void __launch_bounds__(CS_THREADS) consensus_sliced_kernel(const u64 *__restrict__ G, const u32 *__restrict__ T, u32 nt,
+                                                                      const u32 *__restrict__ sreads32, u32 m, int L, int W2, u64 TOT,
+                                                                      u32 *__restrict__ cons32, u32 *__restrict__ deep)
+{
+	__shared__ int sG[CS_SG];
+	const int tid = threadIdx.x;
+	const u64 cb = (u64)blockIdx.x * CS_BLOCK_COLS;
+	const u32 rlo = cb >= (u64)L ? __ldg(&T[(cb - L + 1) / TILE_C]) : 0u;
+	const u32 rhi = __ldg(&T[min((u64)nt - 1, (cb + CS_BLOCK_COLS) / TILE_C)]);
+	const bool staged = rhi - rlo <= (u32)CS_SG;
+	if (staged)
+		for (u32 k = tid; k < rhi - rlo; k += CS_THREADS) sG[k] = (int)(long long)(__ldg(&G[rlo + k]) - cb);
+	__syncthreads();
+	const u64 c0 = cb + (u64)CS_COLS * tid;
+	if (c0 >= (TOT + 31) / 32 * 32) return;
+	const int r0 = CS_COLS * tid;
+	// reads that touch the 16 columns: start in (c0 - L, c0 + 15]
+	u32 lo, hi;
+	if (staged) {
+		u32 a = 0, b = rhi - rlo;
+		while (a < b) { u32 mid = (a + b) >> 1; if (sG[mid] <= r0 - L) a = mid + 1; else b = mid; }
+		lo = a;
+		b = rhi - rlo;
+		while (a < b) { u32 mid = (a + b) >> 1; if (sG[mid] <= r0 + CS_COLS - 1) a = mid + 1; else b = mid; }
+		hi = a;
+		lo += rlo; hi += rlo;
+	} else {
+		lo = c0 >= (u64)L ? upper_bound64(G, m, c0 - L) : 0u;
+		hi = upper_bound64(G, m, c0 + CS_COLS - 1);
+	}
+	if (hi - lo > 4000u) { atomicOr(deep, 1u); return; }
+	const u32 M = 0x55555555u;
+	u32 f[4][CS_PLANES], l[4][3]; // base code order A G C T
+#pragma unroll
+	for (int b = 0; b < 4; b++) {
+#pragma unroll
+		for (int p = 0; p < CS_PLANES; p++) f[b][p] = 0;
+		l[b][0] = l[b][1] = l[b][2] = 0;
+	}
+	auto flush = [&]() {
+#pragma unroll
+		for (int b = 0; b < 4; b++) {
+			u32 a = f[b][0], cy = a & l[b][0];
+			f[b][0] = a ^ l[b][0];
+#pragma unroll
+			for (int p = 1; p < 3; p++) {
+				a = f[b][p];
+				const u32 x = a ^ l[b][p];
+				f[b][p] = x ^ cy;
+				cy = (a & l[b][p]) | (cy & x);
+			}
+#pragma unroll
+			for (int p = 3; p < CS_PLANES; p++) { a = f[b][p]; f[b][p] = a ^ cy; cy &= a; }
+			l[b][0] = l[b][1] = l[b][2] = 0;
+		}
+	};
+	int since = 0;
+	for (u32 i = lo; i < hi; i++) {
+		const int off = staged ? r0 - sG[i - rlo] : (int)((long long)c0 - (long long)__ldg(&G[i])); // column c0 is base `off` of the read
+		const int bit = 2 * off, q = bit >> 5, r = bit & 31;
+		const u32 *rw = sreads32 + (size_t)i * W2;
+		const u32 w0 = (q >= 0 && q < W2) ? __ldg(&rw[q]) : 0u;
+		const u32 w1 = (q + 1 >= 0 && q + 1 < W2) ? __ldg(&rw[q + 1]) : 0u;
+		const u32 x = __funnelshift_r(w0, w1, r);
+		const int klo = max(0, -off), khi = min(CS_COLS, L - off); // columns klo..khi-1 of the tile lie on the read
+		const u32 hm = khi >= 16 ? ~0u : ((1u << (2 * khi)) - 1u), lm = (1u << (2 * klo)) - 1u;
+		const u32 vm = M & hm & ~lm;
+		const u32 e = x & vm, o = (x >> 1) & vm;
+		const u32 h[4] = { vm & ~(e | o), e & ~o, o & ~e, e & o };
+#pragma unroll
+		for (int b = 0; b < 4; b++) {
+			const u32 t0 = l[b][0] & h[b];
+			l[b][0] ^= h[b];
+			const u32 t1 = l[b][1] & t0;
+			l[b][1] ^= t0;
+			l[b][2] ^= t1;
+		}
+		if (++since == 7) { flush(); since = 0; }
+	}
+	flush();
+	// argmax, ties -> A < C < G < T with strict '>' (encoder.cpp:642-648): start from A, then C (code 2), G (1), T (3)
+	u32 best[CS_PLANES], clo = 0, chi = 0;
+#pragma unroll
+	for (int p = 0; p < CS_PLANES; p++) best[p] = f[0][p];
+	const int order[3] = { 2, 1, 3 }; // indices into f: C, G, T
+#pragma unroll
+	for (int s3 = 0; s3 < 3; s3++) {
+		const int b = order[s3];
+		u32 gt = 0, eq = M;
+#pragma unroll
+		for (int p = CS_PLANES - 1; p >= 0; p--) {
+			gt |= eq & f[b][p] & ~best[p];
+			eq &= ~(f[b][p] ^ best[p]);
+		}
+#pragma unroll
+		for (int p = 0; p < CS_PLANES; p++) best[p] = (f[b][p] & gt) | (best[p] & ~gt);
+		// code of base index b in the packed layout is b itself (A0 G1 C2 T3)
+		clo = (b & 1) ? (clo | gt) : (clo & ~gt);
+		chi = (b & 2) ? (chi | gt) : (chi & ~gt);
+	}
+	cons32[c0 / CS_COLS] = clo | (chi << 1);
 }
 
 // ---------------------------------------------------------------------------------------------- pool re-alignment
@@ -841,9 +956,19 @@ int s2_encode(harcgpu_ctx *c)
 		const u32 nt = (u32)(TOT / TILE_C + CONS_T / TILE_C + 2);
 		if (c->alloc(&tile_idx, nt)) return -1;
 		tile_index_kernel<<<KL + cdiv(nt, 256), 256, 0, st>>>(G, m, nt, tile_idx);
-		const size_t csm = (size_t)CONS_R * (1 + 2 * NWv) * sizeof(u32);
-		consensus_kernel<<<KL + cdiv(TOT, CONS_T), CONS_T, csm, st>>>(G, tile_idx, reinterpret_cast<const u32 *>(c->sreads), m, L, 2 * NWv, TOT, cons2);
+		// bit-sliced vote; the column-per-lane kernel only if some column is covered by more reads than the sliced counters hold
+		u32 h_deep = 0;
+		CK(cudaMemsetAsync(d_tot32, 0, 4, st));
+		consensus_sliced_kernel<<<KL + cdiv(TOT, CS_BLOCK_COLS), CS_THREADS, 0, st>>>(G, tile_idx, nt, reinterpret_cast<const u32 *>(c->sreads), m, L,
+		                                                                            2 * NWv, TOT, reinterpret_cast<u32 *>(cons2), d_tot32);
 		CK(cudaGetLastError());
+		CK(cudaMemcpyAsync(&h_deep, d_tot32, 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		if (h_deep || getenv("HARCGPU_CONSENSUS_COLUMNS")) {
+			const size_t csm = (size_t)CONS_R * (1 + 2 * NWv) * sizeof(u32);
+			consensus_kernel<<<KL + cdiv(TOT, CONS_T), CONS_T, csm, st>>>(G, tile_idx, reinterpret_cast<const u32 *>(c->sreads), m, L, 2 * NWv, TOT, cons2);
+			CK(cudaGetLastError());
+		}
 	}
 
 	// ---- pool re-alignment
