@@ -308,6 +308,8 @@ def main():
         lap("get outputs(D2H)")
         d2h[0] = nbytes
 
+    alloc_stats = {}
+
     def barrier():
         if dist is not None:
             dist.barrier()
@@ -320,6 +322,7 @@ def main():
         if sampler:
             sampler.start()
         l0 = harc_b200.launch_count()
+        m0 = ctx.last_ms("cudaMalloc_calls")
         e0.record(stream)
         for _ in range(steps):
             fn()
@@ -334,12 +337,16 @@ def main():
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
+        alloc_stats["cudaMalloc_calls_in_timed_region"] = int(ctx.last_ms("cudaMalloc_calls") - m0)
+        alloc_stats["device_peak_MB"] = ctx.last_ms("peak_MB")
+        alloc_stats["device_cached_MB"] = ctx.last_ms("cached_MB")
         return ms, {p: ph[p] / steps for p in phases}, (harc_b200.launch_count() - l0) // steps
 
     for _ in range(args.warmup):
         es = step_device()
     sampler = ClockSampler(local)
     ms_dev, ph, launches = timed(step_device, args.steps, sampler)
+    alloc_dev = dict(alloc_stats)
     cnt = ctx.counters()
     m, s, u = ctx.reorder_counts()
     if args.no_e2e:
@@ -396,7 +403,7 @@ def main():
         "e2e": {"value": e2e, "unit": "Mreads/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h_clean.numel() + h_N.numel()),
                 "d2h_bytes_per_step": int(d2h[0]),
                 "host_wall_ms": {k: v / args.steps for k, v in host_ms.items()}},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "allocator": dict(alloc_dev),
         "clocks": sampler.summary(),
     }
     if ingest:

@@ -104,6 +104,9 @@ void *harcgpu_stream(harcgpu_ctx *c) { return c ? (void *)c->st : nullptr; }
 double harcgpu_last_ms(harcgpu_ctx *c, const char *phase)
 {
 	if (!c || !phase) return -1;
+	if (!strcmp(phase, "cudaMalloc_calls")) return (double)c->n_cuda_malloc;
+	if (!strcmp(phase, "cached_MB")) return (double)c->cached_bytes / 1048576.0;
+	if (!strcmp(phase, "peak_MB")) return (double)c->peak_bytes / 1048576.0;
 	auto it = c->ms.find(phase);
 	return it == c->ms.end() ? -1.0 : it->second;
 }

@@ -97,6 +97,7 @@ struct harcgpu_ctx {
 	struct Block { void *p; size_t bytes; };
 	std::vector<Block> live, cached;
 	size_t cached_bytes = 0, live_bytes = 0, peak_bytes = 0;
+	unsigned long long n_cuda_malloc = 0; // allocations that reached the driver (harcgpu_last_ms(ctx, "cudaMalloc_calls"))
 	static size_t round_bytes(size_t b) { return b <= (1u << 20) ? (b + 511) / 512 * 512 : (b + (2u << 20) - 1) / (2u << 20) * (2u << 20); }
 	void trim()
 	{
@@ -120,6 +121,7 @@ struct harcgpu_ctx {
 			cached_bytes -= b.bytes;
 		} else {
 			void *q = nullptr;
+			n_cuda_malloc++;
 			cudaError_t e = cudaMalloc(&q, bytes);
 			if (e != cudaSuccess) { // give the cached blocks back to the driver and try once more
 				cudaGetLastError();
