@@ -44,11 +44,30 @@ __global__ void __launch_bounds__(256) pack_kernel(const char *__restrict__ asci
 	const u32 nr = (u32)min((size_t)PACK_RPB, (size_t)n - r0);
 	const size_t bytes = (size_t)nr * line;
 	const char *src = ascii + r0 * line;
-	const size_t nvec = bytes / 16;
-	const uint4 *src4 = reinterpret_cast<const uint4 *>(src);
-	for (size_t v = threadIdx.x; v < nvec; v += blockDim.x) stage4[v] = __ldg(&src4[v]);
-	for (size_t b = nvec * 16 + threadIdx.x; b < bytes; b += blockDim.x) stage[b] = src[b];
-	__syncthreads();
+	if (bytes % 16 == 0) {
+		// a full block: its 64 lines are one 16-byte-aligned span, fetched by ONE bulk copy of the TMA unit
+		// (cp.async.bulk, global -> shared, completion counted in bytes on an mbarrier) issued by one thread
+		__shared__ __align__(8) unsigned long long bar;
+		const u32 bar_a = (u32)__cvta_generic_to_shared(&bar), dst_a = (u32)__cvta_generic_to_shared(stage);
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((u32)bytes) : "memory");
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a), "l"(src),
+			             "r"((u32)bytes), "r"(bar_a)
+			             : "memory");
+		}
+		__syncthreads(); // the barrier is initialised before anybody polls it
+		u32 done = 0;
+		while (!done)
+			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar_a) : "memory");
+	} else {
+		const size_t nvec = bytes / 16;
+		const uint4 *src4 = reinterpret_cast<const uint4 *>(src);
+		for (size_t v = threadIdx.x; v < nvec; v += blockDim.x) stage4[v] = __ldg(&src4[v]);
+		for (size_t b = nvec * 16 + threadIdx.x; b < bytes; b += blockDim.x) stage[b] = src[b];
+		__syncthreads();
+	}
 	for (u32 w = threadIdx.x; w < nr * (u32)NWo; w += blockDim.x) {
 		const u32 r = w / NWo, k = w % NWo;
 		const u32 o = r * (u32)line + 32 * k; // byte offset of the word's first base
