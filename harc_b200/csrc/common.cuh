@@ -40,6 +40,19 @@ __device__ __forceinline__ u64 getbits(const u64 *w, int words, int pos, int n)
 // mask with the low `n` bits set, n clamped to [0,64]
 __device__ __forceinline__ u64 lowmask(int n) { return n >= 64 ? ~0ull : (n <= 0 ? 0ull : ((1ull << n) - 1)); }
 
+// base t: 2-bit code c -> 3-bit code 2c at bits 3t (nb <= 21 bases): the groups are moved apart in five doubling steps
+__device__ __forceinline__ u64 spread2to3(u64 k2, int nb)
+{
+	u64 x = nb < 32 ? k2 & ((1ull << (2 * nb)) - 1) : k2;
+	// (masks generated and checked against the per-base loop for every nb <= 21)
+	x = (x & 0x00000000ffffffffull) | ((x & 0x000003ff00000000ull) << 16); // bases 16..20 move by 16
+	x = (x & 0x03ff00000000ffffull) | ((x & 0x00000000ffff0000ull) << 8);  // bases with bit 3 set move by 8
+	x = (x & 0x00ff0000ff0000ffull) | ((x & 0x030000ff0000ff00ull) << 4);  // bit 2: by 4
+	x = (x & 0x300f00f00f00f00full) | ((x & 0x00f00f00f00f00f0ull) << 2);  // bit 1: by 2
+	x = (x & 0x30c30c30c30c30c3ull) | ((x & 0x030c30c30c30c30cull) << 1);  // bit 0: by 1
+	return x << 1;
+}
+
 // ---- the key table that stands in for BooPHF (BooPHF.h:970-1008) ------------------------------------------------
 // A key is mixed by one 64-bit multiply (a bijection, so equal keys <=> equal mixed keys); the table is ORDERED by the
 // mixed key: the home bucket of a key is the top bits of its mixed value, and the bins are placed in mixed-key order

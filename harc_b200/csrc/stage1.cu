@@ -134,18 +134,19 @@ __global__ void __launch_bounds__(256) keys_kernel(const u64 *__restrict__ reads
 	ids[i] = i;
 }
 
-// stage II keys (encoder.cpp:893-911): the reference's 3-bit code of base b is 2*code2 + nflag
+// stage II keys (encoder.cpp:893-911): the reference's 3-bit code of base b is 2*code2 + nflag.  The window's 2-bit
+// codes and N flags (bit 2b of the flag words) are cut out with two shifts each and moved apart by spread2to3.
 __global__ void __launch_bounds__(256) keys3_kernel(const u64 *__restrict__ r2, const u64 *__restrict__ rN, u32 n, int words, int ds,
                                                     int de, u64 *__restrict__ keys, u32 *__restrict__ ids)
 {
 	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	u64 key = 0;
-	for (int b = ds; b <= de; b++) {
-		u64 c2 = (__ldg(&r2[(size_t)i * words + (b >> 5)]) >> (2 * (b & 31))) & 3ull;
-		u64 nf = (__ldg(&rN[(size_t)i * words + (b >> 5)]) >> (2 * (b & 31))) & 1ull;
-		key |= ((c2 << 1) | nf) << (3 * (b - ds));
-	}
+	const int nb = de - ds + 1, bitpos = 2 * ds, q = bitpos >> 6, sh = bitpos & 63;
+	const u64 *a = r2 + (size_t)i * words, *b = rN + (size_t)i * words;
+	u64 c2 = __ldg(&a[q]) >> sh, nf = __ldg(&b[q]) >> sh;
+	if (sh && q + 1 < words) { c2 |= __ldg(&a[q + 1]) << (64 - sh); nf |= __ldg(&b[q + 1]) << (64 - sh); }
+	// spread2to3 puts 2*c at bits 3t: for the flags (c = 0 or 1 in the low bit of the pair) that is flag << 1
+	const u64 key = spread2to3(c2, nb) | (spread2to3(nf & 0x5555555555555555ull, nb) >> 1);
 	keys[i] = key_mix(key);
 	ids[i] = i;
 }

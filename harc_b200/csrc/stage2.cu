@@ -353,21 +353,10 @@ struct PoolArgs {
 	u64 *best;
 	u64 rank_bits; // rank << RANK_SHIFT
 	const u32 *bloom; u32 bloom_mask;
-	const u32 *T; // tile index (TILE_C == PROBE_T)
+	const u32 *T; // tile index
+	u32 nt;       // its entries
+	u64 cwords;   // words of cons2 incl. the two zero words at its end
 };
-
-// base t: 2-bit code c -> 3-bit code 2c at bits 3t (nb <= 21 bases): the groups are moved apart in five doubling steps
-__device__ __forceinline__ u64 spread2to3(u64 k2, int nb)
-{
-	u64 x = nb < 32 ? k2 & ((1ull << (2 * nb)) - 1) : k2;
-	// (masks generated and checked against the per-base loop for every nb <= 21)
-	x = (x & 0x00000000ffffffffull) | ((x & 0x000003ff00000000ull) << 16); // bases 16..20 move by 16
-	x = (x & 0x03ff00000000ffffull) | ((x & 0x00000000ffff0000ull) << 8);  // bases with bit 3 set move by 8
-	x = (x & 0x00ff0000ff0000ffull) | ((x & 0x030000ff0000ff00ull) << 4);  // bit 2: by 4
-	x = (x & 0x300f00f00f00f00full) | ((x & 0x00f00f00f00f00f0ull) << 2);  // bit 1: by 2
-	x = (x & 0x30c30c30c30c30c3ull) | ((x & 0x030c30c30c30c30cull) << 1);  // bit 0: by 1
-	return x << 1;
-}
 
 // Blocked Bloom filter over the keys of both pool dictionaries (one 32-bit word per key, two bits in it): most window
 // keys of the consensus are in neither dictionary, and the filter (a few MB, L2 resident) answers those without
@@ -388,83 +377,122 @@ __global__ void __launch_bounds__(256) bloom_insert_kernel(const u64 *__restrict
 	atomicOr(&bloom[w], b);
 }
 
-constexpr int PROBE_T = TILE_C; // window starts per block
-constexpr int PROBE_R = 768;  // stream reads whose start columns are staged per block
+// One thread per PP_CPT consecutive window starts.  The consensus bits of the block's span and the start columns of the
+// reads around it are staged in shared memory; a thread computes the four window keys of its first column from scratch
+// and then ROLLS them: a forward key drops its first base and takes the next consensus base on top, a reverse key (the
+// reverse complement of a window that also moves right) shifts up and takes the complemented base at the bottom -- a
+// handful of instructions per key and column instead of two 64-bit extractions, a pair reversal and a five-step spread.
+constexpr int PP_CPT = 8;
+constexpr int PP_THREADS = 128;
+constexpr int PP_COLS = PP_CPT * PP_THREADS; // 1024 window starts per block = 8 cells of the tile index
+constexpr int PP_R = 2048;                   // stream reads whose start columns are staged per block
+constexpr int PP_CW = (PP_COLS + 256) / 32 + 2; // consensus words of the block's span (columns + read length)
 template <int NW>
-__global__ void __launch_bounds__(PROBE_T) pool_probe_kernel(PoolArgs a)
+__global__ void __launch_bounds__(PP_THREADS) pool_probe_kernel(PoolArgs a)
 {
-	__shared__ int sG[PROBE_R];
+	__shared__ int sG[PP_R];
+	__shared__ u64 sC[PP_CW];
 	const int tid = threadIdx.x;
-	const u64 g0 = (u64)blockIdx.x * PROBE_T, g = g0 + tid;
+	const u64 gb = (u64)blockIdx.x * PP_COLS;
 	const int L = a.L;
 	const u64 glast = a.TOT - L; // last window start; the launch guarantees TOT >= L
-	// which contig does column g belong to?  r = last read with G[r] <= g.  The start columns of the reads around the
-	// tile (from the last read before it to the first one behind it, via the tile index) are staged and searched.
-	const u32 t0 = __ldg(&a.T[blockIdx.x]);
-	const u32 r0 = t0 ? t0 - 1 : 0u, r1 = __ldg(&a.T[blockIdx.x + 1]);
-	const bool staged = r1 - r0 <= (u32)PROBE_R;
-	if (staged) {
-		for (u32 k = tid; k < r1 - r0; k += PROBE_T) sG[k] = (int)(long long)(__ldg(&a.G[r0 + k]) - g0);
-		__syncthreads();
+	for (int k = tid; k < PP_CW; k += PP_THREADS) {
+		const u64 wi = gb / 32 + k;
+		sC[k] = wi < a.cwords ? __ldg(&a.cons2[wi]) : 0ull;
 	}
-	if (g > glast) return;
+	// r = last read with G[r] <= g tells which contig column g belongs to: the start columns of the reads around the block
+	// (from the last read before it to the first one behind it, via the tile index) are staged and searched
+	const u32 cell = blockIdx.x * (PP_COLS / TILE_C);
+	const u32 t0 = __ldg(&a.T[min(cell, a.nt - 1)]);
+	const u32 r0 = t0 ? t0 - 1 : 0u, r1 = __ldg(&a.T[min(cell + PP_COLS / TILE_C, a.nt - 1)]);
+	const bool staged = r1 - r0 <= (u32)PP_R;
+	if (staged)
+		for (u32 k = tid; k < r1 - r0; k += PP_THREADS) sG[k] = (int)(long long)(__ldg(&a.G[r0 + k]) - gb);
+	__syncthreads();
+	const int rel0 = PP_CPT * tid;
+	if (gb + rel0 > glast) return;
 	u32 r;
 	if (staged) {
 		u32 lo = 0, hi = r1 - r0;
-		while (lo < hi) { u32 mid = (lo + hi) >> 1; if (sG[mid] <= tid) lo = mid + 1; else hi = mid; }
+		while (lo < hi) { u32 mid = (lo + hi) >> 1; if (sG[mid] <= rel0) lo = mid + 1; else hi = mid; }
 		r = r0 + lo - 1;
-	} else r = upper_bound64(a.G, a.m, g) - 1;
-	u32 c = __ldg(&a.cid[r]);
-	u32 next = c + 1 < a.NC ? __ldg(&a.cstart[c + 1]) : a.m;
-	if (next == a.m || next % a.per == 0) return; // last contig of its thread range: written without alignment (encoder.cpp:438-441)
-	if (g + L > __ldg(&a.G[next])) return;        // j <= ref.size()-readlen (encoder.cpp:252)
-	u64 w[NW], rc[NW];
-	bool have_w = false, have_rc = false;
-	// the four window keys and their Bloom words first, so that the four L2 round trips overlap
-	u64 k3s[4];
-	u32 bword[4], bbits[4];
+	} else r = upper_bound64(a.G, a.m, gb + rel0) - 1;
+	auto base_at = [&](int rel) -> u64 { return (sC[rel >> 5] >> (2 * (rel & 31))) & 3ull; }; // consensus base of column gb + rel
+	auto bits_at = [&](int rel, int n) -> u64 { // 2n bits from column gb + rel on (n <= 32)
+		const int q = rel >> 5, sh = 2 * (rel & 31);
+		u64 v = sC[q] >> sh;
+		if (sh) v |= sC[q + 1] << (64 - sh);
+		return n < 32 ? v & ((1ull << (2 * n)) - 1) : v;
+	};
+	const int nb0 = a.d[0].dend - a.d[0].dstart + 1, nb1 = a.d[1].dend - a.d[1].dstart + 1;
+	u64 k3s[4] = { 0, 0, 0, 0 };
+	u32 c_cached = 0xffffffffu;
+	bool col_ok = false;
+	u64 g_limit = 0; // a window may start at g only if g + L <= g_limit (start of the next contig)
+	for (int t = 0; t < PP_CPT; t++) {
+		const int rel = rel0 + t;
+		const u64 g = gb + rel;
+		if (g > glast) break;
+		// the four window keys: forward dict 0, forward dict 1, reverse dict 0, reverse dict 1 (encoder.cpp:270, 338)
 #pragma unroll
-	for (int q = 0; q < 4; q++) { // forward dict 0, forward dict 1, reverse dict 0, reverse dict 1 (encoder.cpp:270, 338)
-		const int l = q & 1;
-		const bool rev = q >= 2;
-		const DictView &dv = a.d[l];
-		const int nb = dv.dend - dv.dstart + 1;
-		u64 k2;
-		if (!rev) k2 = getbits_g(a.cons2, 2 * (g + dv.dstart), 2 * nb);
-		else {
-			k2 = getbits_g(a.cons2, 2 * (g + L - 1 - dv.dend), 2 * nb);
-			k2 = revpairs64(~k2 & lowmask(2 * nb)) >> (64 - 2 * nb);
+		for (int q = 0; q < 4; q++) {
+			const int l = q & 1, nb = l ? nb1 : nb0, ds = a.d[l].dstart, de = a.d[l].dend;
+			if (t == 0) {
+				if (q < 2) k3s[q] = spread2to3(bits_at(rel + ds, nb), nb);
+				else {
+					const u64 k2 = bits_at(rel + L - 1 - de, nb);
+					k3s[q] = spread2to3(revpairs64(~k2 & lowmask(2 * nb)) >> (64 - 2 * nb), nb);
+				}
+			} else if (q < 2) k3s[q] = (k3s[q] >> 3) | (base_at(rel + de) << (3 * (nb - 1) + 1));
+			else k3s[q] = ((k3s[q] << 3) & ((1ull << (3 * nb)) - 1)) | ((base_at(rel + L - 1 - ds) ^ 3ull) << 1);
 		}
-		k3s[q] = spread2to3(k2, nb);
-		u32 bw;
-		bloom_pos(k3s[q], l, a.bloom_mask, bw, bbits[q]);
-		bword[q] = __ldg(&a.bloom[bw]);
-	}
-#pragma unroll
-	for (int q = 0; q < 4; q++) {
-		const int l = q & 1;
-		const bool rev = q >= 2;
-		const DictView &dv = a.d[l];
-		const u64 k3 = k3s[q];
-		if ((bword[q] & bbits[q]) != bbits[q]) continue;
-		u32 bstart, bsize;
-		if (!dict_lookup(dv, k3, bstart, bsize)) continue;
-		if (!have_w) { load_window<NW>(a.cons2, g, L, w); have_w = true; }
-		if (rev && !have_rc) {
-			u64 t[NW];
-			reverse2<NW>(w, L, t);
-#pragma unroll
-			for (int k = 0; k < NW; k++) rc[k] = t[k] ^ lowmask(2 * L - 64 * k);
-			have_rc = true;
+		// may a window start here?  (advance r to the last read that starts at or before g)
+		if (staged) { while (r + 1 < r1 && sG[r + 1 - r0] <= rel) r++; }
+		else { while (r + 1 < a.m && __ldg(&a.G[r + 1]) <= g) r++; }
+		const u32 c = __ldg(&a.cid[r]);
+		if (c != c_cached) {
+			c_cached = c;
+			const u32 next = c + 1 < a.NC ? __ldg(&a.cstart[c + 1]) : a.m;
+			// the last contig of a thread range is written without alignment (encoder.cpp:438-441)
+			col_ok = !(next == a.m || next % a.per == 0);
+			g_limit = col_ok ? __ldg(&a.G[next]) : 0ull;
 		}
-		const u32 tlo = bsize > (u32)a.maxsearch ? bsize - (u32)a.maxsearch : 0u;
-		for (u32 t = bsize; t-- > tlo;) { // from the tail, no break: every read of the bin within thresh_s is taken (293-317)
-			const u32 rid = bin_entry(dv, bstart, bsize, t);
-			const u64 *p2 = a.pool + (size_t)rid * NW, *pn = a.poolN + (size_t)rid * NW;
-			int d = 0;
+		if (!col_ok || g + L > g_limit) continue; // j <= ref.size()-readlen (encoder.cpp:252)
+		// Bloom words of the four keys first, so that the four L2 round trips overlap
+		u32 bword[4], bbits[4];
 #pragma unroll
-			for (int k = 0; k < NW; k++) d += __popcll((rev ? rc[k] : w[k]) ^ __ldg(&p2[k])) + __popcll(__ldg(&pn[k]));
-			if (d <= a.thresh_s) atomicMin(&a.best[rid], a.rank_bits | (g << 2) | (u64)q);
+		for (int q = 0; q < 4; q++) {
+			u32 bw;
+			bloom_pos(k3s[q], q & 1, a.bloom_mask, bw, bbits[q]);
+			bword[q] = __ldg(&a.bloom[bw]);
+		}
+		u64 w[NW], rc[NW];
+		bool have_w = false, have_rc = false;
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			if ((bword[q] & bbits[q]) != bbits[q]) continue;
+			const int l = q & 1;
+			const bool rev = q >= 2;
+			const DictView &dv = a.d[l];
+			u32 bstart, bsize;
+			if (!dict_lookup(dv, k3s[q], bstart, bsize)) continue;
+			if (!have_w) { load_window<NW>(a.cons2, g, L, w); have_w = true; }
+			if (rev && !have_rc) {
+				u64 tt[NW];
+				reverse2<NW>(w, L, tt);
+#pragma unroll
+				for (int k = 0; k < NW; k++) rc[k] = tt[k] ^ lowmask(2 * L - 64 * k);
+				have_rc = true;
+			}
+			const u32 tlo = bsize > (u32)a.maxsearch ? bsize - (u32)a.maxsearch : 0u;
+			for (u32 e = bsize; e-- > tlo;) { // from the tail, no break: every read of the bin within thresh_s is taken (293-317)
+				const u32 rid = bin_entry(dv, bstart, bsize, e);
+				const u64 *p2 = a.pool + (size_t)rid * NW, *pn = a.poolN + (size_t)rid * NW;
+				int d = 0;
+#pragma unroll
+				for (int k = 0; k < NW; k++) d += __popcll((rev ? rc[k] : w[k]) ^ __ldg(&p2[k])) + __popcll(__ldg(&pn[k]));
+				if (d <= a.thresh_s) atomicMin(&a.best[rid], a.rank_bits | (g << 2) | (u64)q);
+			}
 		}
 	}
 }
@@ -877,10 +905,10 @@ static int load_pool_impl(harcgpu_ctx *c, const char *s_ascii, const u32 *order_
 	for (int l = 0; l < 2; l++)
 		if (build_dict(c, c->d2[l], c->pool, c->poolN, P, c->NW, ds[l], de[l], 3)) return -1;
 	{
-		// Bloom filter over both dictionaries: >= 16 bits per key
+		// Bloom filter over both dictionaries: >= 8 bits per key (it has to stay in L2 next to the streams of the kernel)
 		const u64 nk = (u64)c->d2[0].numkeys + c->d2[1].numkeys;
 		u64 words = 1024;
-		while (words * 32 < 16 * nk) words <<= 1;
+		while (words * 32 < 8 * nk) words <<= 1;
 		c->release(c->bloom2);
 		c->bloom2 = nullptr;
 		if (c->alloc(&c->bloom2, words)) return -1;
@@ -923,7 +951,7 @@ int s2_encode(harcgpu_ctx *c)
 	u32 *ns = nullptr, *ex = nullptr, *nat_idx = nullptr, *cs = nullptr, *cid = nullptr, *cstart = nullptr, *d_tot32 = nullptr;
 	u64 *inc = nullptr, *G = nullptr, *scan_tmp = nullptr, *d_tot64 = nullptr, *cons2 = nullptr;
 	u32 *tile_idx = nullptr;
-	u32 NC = 0;
+	u32 NC = 0, nt_host = 0;
 	u64 TOT = 0;
 	size_t scan_n = std::max<size_t>(std::max<size_t>(m, P), 1);
 	if (c->alloc(&d_tot32, 4) || c->alloc(&d_tot64, 2)) return -1;
@@ -954,6 +982,7 @@ int s2_encode(harcgpu_ctx *c)
 	if (m) {
 		// tile index: entries 0 .. TOT/TILE_C + CONS_T/TILE_C (the consensus tiles look one tile past their end)
 		const u32 nt = (u32)(TOT / TILE_C + CONS_T / TILE_C + 2);
+		nt_host = nt;
 		if (c->alloc(&tile_idx, nt)) return -1;
 		tile_index_kernel<<<KL + cdiv(nt, 256), 256, 0, st>>>(G, m, nt, tile_idx);
 		// bit-sliced vote; the column-per-lane kernel only if some column is covered by more reads than the sliced counters hold
@@ -991,9 +1020,9 @@ int s2_encode(harcgpu_ctx *c)
 		}
 		a.L = L; a.thresh_s = c->p.thresh_s; a.maxsearch = c->p.maxsearch; a.best = best;
 		a.rank_bits = (u64)(c->shard_world > 1 ? c->shard_rank : 0) << RANK_SHIFT;
-		a.bloom = c->bloom2; a.bloom_mask = c->bloom2_mask; a.T = tile_idx;
+		a.bloom = c->bloom2; a.bloom_mask = c->bloom2_mask; a.T = tile_idx; a.nt = nt_host; a.cwords = cwords + 2;
 		u64 nwin = TOT - L + 1;
-		DISPATCH_NW(NWv, (pool_probe_kernel<NW><<<KL + cdiv(nwin, PROBE_T), PROBE_T, 0, st>>>(a)));
+		DISPATCH_NW(NWv, (pool_probe_kernel<NW><<<KL + cdiv(nwin, PP_COLS), PP_THREADS, 0, st>>>(a)));
 		CK(cudaGetLastError());
 	}
 	if (P && c->shard_world > 1) {
