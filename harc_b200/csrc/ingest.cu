@@ -87,24 +87,24 @@ __global__ void __launch_bounds__(256) seq_offset_kernel(const char *__restrict_
 // A warp works on ING_RPW consecutive records at a time and issues the byte loads of all of them before it looks at
 // any (the kernel is otherwise bound by the latency of one short dependent chain per warp).
 constexpr int ING_RPW = 4;  // records per warp and round
-constexpr int ING_MAXT = 8; // 32-byte slices of a line: readlen + 1 <= 256
+// T = 32-byte slices of a line (readlen + 1 <= 256 -> T <= 8): a template parameter so that no dead slice is issued
+template <int T>
 __global__ void __launch_bounds__(256) classify_kernel(const char *__restrict__ buf, u64 nbytes, const u64 *__restrict__ seq_off, u64 nrec,
                                                        int L, u32 *__restrict__ isN, unsigned long long *__restrict__ err)
 {
 	const u64 r0 = (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * ING_RPW;
 	const int lane = threadIdx.x & 31;
 	if (r0 >= nrec) return;
-	const int T = (L + 1 + 31) / 32;
 	u64 off[ING_RPW];
-	unsigned char ch[ING_RPW][ING_MAXT];
+	unsigned char ch[ING_RPW][T];
 #pragma unroll
 	for (int k = 0; k < ING_RPW; k++) off[k] = r0 + k < nrec ? __ldg(&seq_off[r0 + k]) : nbytes;
 #pragma unroll
 	for (int k = 0; k < ING_RPW; k++)
 #pragma unroll
-		for (int t = 0; t < ING_MAXT; t++) {
+		for (int t = 0; t < T; t++) {
 			const u64 p = off[k] + lane + 32 * t;
-			ch[k][t] = (t < T && p < nbytes) ? (unsigned char)__ldg(&buf[p]) : (unsigned char)'\n'; // the end of the file ends a line
+			ch[k][t] = p < nbytes ? (unsigned char)__ldg(&buf[p]) : (unsigned char)'\n'; // the end of the file ends a line
 		}
 #pragma unroll
 	for (int k = 0; k < ING_RPW; k++) {
@@ -113,9 +113,9 @@ __global__ void __launch_bounds__(256) classify_kernel(const char *__restrict__ 
 		bool hasN = false;
 		int nlpos = 0x7fffffff; // first newline / end of file inside the first L + 1 bytes of the line
 #pragma unroll
-		for (int t = 0; t < ING_MAXT; t++) {
+		for (int t = 0; t < T; t++) {
 			const int i = lane + 32 * t;
-			if (t < T && i <= L) {
+			if (i <= L) {
 				if (ch[k][t] == '\n') nlpos = min(nlpos, i);
 				else if (i < L && ch[k][t] == 'N') hasN = true;
 			}
@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(256) classify_kernel(const char *__restrict__ 
 	}
 }
 
+// H = 128-base halves of a read (readlen <= 128 -> 1, else 2)
+template <int H>
 __global__ void __launch_bounds__(256) emit_kernel(const char *__restrict__ buf, u64 nbytes, const u64 *__restrict__ seq_off, u64 nrec, int L,
                                                    int NW, const u32 *__restrict__ isN, const u32 *__restrict__ exN, u64 *__restrict__ reads,
                                                    char *__restrict__ outN, u32 *__restrict__ orderN)
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const char *__restrict__ buf,
 	// lane k packs output bytes k and k + 32 of a read (bases 4k .. 4k+3): up to 8 input bytes per record
 	u64 off[ING_RPW];
 	u32 nb[ING_RPW], fl[ING_RPW];
-	unsigned char ch[ING_RPW][8];
+	unsigned char ch[ING_RPW][4 * H];
 #pragma unroll
 	for (int k = 0; k < ING_RPW; k++) {
 		const bool ok = r0 + k < nrec;
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const char *__restrict__ buf,
 #pragma unroll
 	for (int k = 0; k < ING_RPW; k++)
 #pragma unroll
-		for (int t = 0; t < 8; t++) {
+		for (int t = 0; t < 4 * H; t++) {
 			const int i = 4 * (lane + 32 * (t >> 2)) + (t & 3);
 			ch[k][t] = (r0 + k < nrec && i < L) ? (unsigned char)__ldg(&buf[off[k] + i]) : (unsigned char)'A';
 		}
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const char *__restrict__ buf,
 		if (fl[k]) {
 			char *dst = outN + (size_t)nb[k] * (L + 1);
 #pragma unroll
-			for (int t = 0; t < 8; t++) {
+			for (int t = 0; t < 4 * H; t++) {
 				const int i = 4 * (lane + 32 * (t >> 2)) + (t & 3);
 				if (i < L) dst[i] = (char)ch[k][t];
 			}
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const char *__restrict__ buf,
 #pragma unroll
 			for (int h = 0; h < 2; h++) {
 				const int kb = lane + 32 * h; // output byte
-				if (kb < 8 * NW) {
+				if (h < H && kb < 8 * NW) {
 					u32 v = 0;
 #pragma unroll
 					for (int t = 0; t < 4; t++) {
@@ -250,7 +252,17 @@ int ing_ingest(harcgpu_ctx *c, const char *d_fastq, u64 nbytes, u64 *total_reads
 		if (c->alloc(&scan_tmp, scan_tmp_elems(nrec))) return -1;
 		CK(cudaMemsetAsync(err, 0xff, 8, st));
 		seq_offset_kernel<<<KL + (unsigned)ntiles, 256, 0, st>>>(d_fastq, nbytes, base, nrec, seq_off);
-		classify_kernel<<<KL + cdiv((nrec + ING_RPW - 1) / ING_RPW * 32, 256), 256, 0, st>>>(d_fastq, nbytes, seq_off, nrec, L, isN, err);
+		const unsigned cg = cdiv((nrec + ING_RPW - 1) / ING_RPW * 32, 256);
+		switch ((L + 1 + 31) / 32) {
+		case 1: classify_kernel<1><<<KL + cg, 256, 0, st>>>(d_fastq, nbytes, seq_off, nrec, L, isN, err); break;
+		case 2: classify_kernel<2><<<KL + cg, 256, 0, st>>>(d_fastq, nbytes, seq_off, nrec, L, isN, err); break;
+		case 3: classify_kernel<3><<<KL + cg, 256, 0, st>>>(d_fastq, nbytes, seq_off, nrec, L, isN, err); break;
+		case 4: classify_kernel<4><<<KL + cg, 256, 0, st>>>(d_fastq, nbytes, seq_off, nrec, L, isN, err); break;
+		case 5: classify_kernel<5><<<KL + cg, 256, 0, st>>>(d_fastq, nbytes, seq_off, nrec, L, isN, err); break;
+		case 6: classify_kernel<6><<<KL + cg, 256, 0, st>>>(d_fastq, nbytes, seq_off, nrec, L, isN, err); break;
+		case 7: classify_kernel<7><<<KL + cg, 256, 0, st>>>(d_fastq, nbytes, seq_off, nrec, L, isN, err); break;
+		default: classify_kernel<8><<<KL + cg, 256, 0, st>>>(d_fastq, nbytes, seq_off, nrec, L, isN, err); break;
+		}
 		CK(cudaGetLastError());
 		if (exclusive_scan_u32(isN, exN, nrec, scan_tmp, d_tot32, st)) return -1;
 		unsigned long long herr = 0;
@@ -268,7 +280,9 @@ int ing_ingest(harcgpu_ctx *c, const char *d_fastq, u64 nbytes, u64 *total_reads
 	if (c->alloc(&c->ing_N, (size_t)nN * (L + 1) + 16) || c->alloc(&c->ing_orderN, nN)) return -1;
 	c->ing_nN = nN;
 	if (nrec) {
-		emit_kernel<<<KL + cdiv((nrec + ING_RPW - 1) / ING_RPW * 32, 256), 256, 0, st>>>(d_fastq, nbytes, seq_off, nrec, L, c->NW, isN, exN, c->reads, c->ing_N, c->ing_orderN);
+		const unsigned eg = cdiv((nrec + ING_RPW - 1) / ING_RPW * 32, 256);
+		if (L <= 128) emit_kernel<1><<<KL + eg, 256, 0, st>>>(d_fastq, nbytes, seq_off, nrec, L, c->NW, isN, exN, c->reads, c->ing_N, c->ing_orderN);
+		else emit_kernel<2><<<KL + eg, 256, 0, st>>>(d_fastq, nbytes, seq_off, nrec, L, c->NW, isN, exN, c->reads, c->ing_N, c->ing_orderN);
 		CK(cudaGetLastError());
 	}
 	c->toc("ingest");
