@@ -67,15 +67,17 @@ __global__ void __launch_bounds__(256) rs_gscan_kernel(const u32 *__restrict__ g
 
 struct RsSmem {
 	u64 key[RS_TILE];
-	u32 val[RS_TILE];
-	u32 wh[RS_WARPS][256]; // per warp: count, then start inside the tile's run of the digit
+	union { // the per-warp digit counters are dead once every pair knows its place in the tile
+		u32 val[RS_TILE];
+		u32 wh[RS_WARPS][256]; // per warp: count, then start inside the tile's run of the digit
+	};
 	u32 dstart[256];       // start of the digit's run inside the tile
 	u64 gbase[256];        // global index of the first pair of the digit's run of this tile
 	u32 wsum[8];
 	u32 ticket;
 };
 
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
+__global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
                                                                 u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, size_t n, int shift,
                                                                 u32 dmask, const u32 *__restrict__ gstart, u64 *lookback, u32 *ticket_ctr)
 {
@@ -111,17 +113,24 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__res
 	__syncthreads();
 	volatile u64 *lb = lookback;
 	if (tid < 256) lb[(size_t)tile * 256 + tid] = (u64)s.dstart[tid] | RS_PARTIAL;
+	// the matches of all items first (independent of each other), then the counter updates in item order
+	u32 peers[RS_ITEMS];
+#pragma unroll
+	for (int i = 0; i < RS_ITEMS; i++) {
+		const u32 p = (u32)w * (32 * RS_ITEMS) + 32 * i + lane;
+		const u32 d = p < tile_n ? ((u32)(key[i] >> shift) & dmask) : (256u + lane); // pairs behind the end match nobody
+		peers[i] = __match_any_sync(0xffffffffu, d);
+	}
 #pragma unroll
 	for (int i = 0; i < RS_ITEMS; i++) {
 		const u32 p = (u32)w * (32 * RS_ITEMS) + 32 * i + lane;
 		const bool valid = p < tile_n;
-		const u32 d = valid ? ((u32)(key[i] >> shift) & dmask) : (256u + lane); // pairs behind the end match nobody
-		const u32 peers = __match_any_sync(0xffffffffu, d);
-		const int leader = __ffs(peers) - 1;
+		const u32 d = (u32)(key[i] >> shift) & dmask;
+		const int leader = __ffs(peers[i]) - 1;
 		u32 old = 0;
-		if (lane == leader && valid) { old = s.wh[w][d]; s.wh[w][d] = old + __popc(peers); }
+		if (lane == leader && valid) { old = s.wh[w][d]; s.wh[w][d] = old + __popc(peers[i]); }
 		old = __shfl_sync(0xffffffffu, old, leader);
-		rank[i] = old + __popc(peers & lt);
+		rank[i] = old + __popc(peers[i] & lt);
 	}
 	__syncthreads();
 	// digit tid (the first 256 threads): starts of the warps' runs inside the digit's run, look-back, then the start of
@@ -155,13 +164,18 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__res
 	}
 	__syncthreads();
 #pragma unroll
+	for (int i = 0; i < RS_ITEMS; i++) { // place of the pair in the tile, in digit order
+		const u32 p = (u32)w * (32 * RS_ITEMS) + 32 * i + lane;
+		const u32 d = (u32)(key[i] >> shift) & dmask;
+		if (p < tile_n) rank[i] += s.dstart[d] + s.wh[w][d];
+	}
+	__syncthreads(); // the counters are dead: their memory takes the values now
+#pragma unroll
 	for (int i = 0; i < RS_ITEMS; i++) {
 		const u32 p = (u32)w * (32 * RS_ITEMS) + 32 * i + lane;
 		if (p < tile_n) {
-			const u32 d = (u32)(key[i] >> shift) & dmask;
-			const u32 q = s.dstart[d] + s.wh[w][d] + rank[i];
-			s.key[q] = key[i];
-			s.val[q] = __ldg(&vals_in[tbase + p]);
+			s.key[rank[i]] = key[i];
+			s.val[rank[i]] = __ldg(&vals_in[tbase + p]);
 		}
 	}
 	__syncthreads();
