@@ -256,8 +256,11 @@ struct Probe {
 // G = lanes per walker: 32 (one walker per warp, 8 shifts per round) or 16 (two walkers per warp, 4 shifts per round;
 // the two walkers share every instruction of a round while they are in the same phase).  `sub` is the lane inside the
 // walker's group; every warp-level primitive below is restricted to the group (gmask).
+#ifndef WALK_MB
+#define WALK_MB 8 // blocks per SM the registers are bounded for when NW <= 4 (8 -> 64 registers)
+#endif
 template <int NW, int G>
-__global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? 8 : 4) walk_kernel(WalkArgs a)
+__global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_kernel(WalkArgs a)
 {
 	constexpr int W2 = 2 * NW;
 	constexpr int WPW = 32 / G;          // walkers per warp
