@@ -1,13 +1,14 @@
 // Stage I of HARC -- hash-based read reordering (reference: src/reorder.cpp) -- as sm_100a kernels.
 //
-//   K1 pack2_kernel      ASCII lines -> 2 bits/base                     reorder.cpp:203-209, 240-263
-//   K2 keys_kernel       (read & mask) >> 2*dict_start                  reorder.cpp:284-302
-//   K3 radix sort + heads/scan/scatter + table insert                   reorder.cpp:305-390 (sort, dedup, MPHF, CSR fill)
-//   K4 walk_kernel       warp-per-chain greedy walk                     reorder.cpp:434-703, 863-915
-//   K5 finalize (chunk sort, partition) + unpack_kernel                 reorder.cpp:722-830
+//   K1 pack_kernel       ASCII lines -> 2 bits/base (one TMA bulk copy per block)   reorder.cpp:203-209, 240-263
+//   K2 keys_kernel       (read & mask) >> 2*dict_start, mixed by one multiply        reorder.cpp:284-302
+//   K3 radix sort (sort.cu) + heads/scan/bins + prefix-maximum table placement       reorder.cpp:305-390 (sort, dedup, MPHF, CSR fill)
+//   K4 walk_kernel       warp-per-chain greedy walk (walk.cu)                        reorder.cpp:434-703, 863-915
+//   K5 finalize (chunk sort, partition; walk.cu) + unpack_kernel                     reorder.cpp:722-830
 //
-// Data layout in HBM: reads[n][NW] u64 (NW = ceil(2L/64)); per dictionary the canonical CSR (keys, start, ids) and a
-// 16-byte-slot open-addressing table at load factor <= 0.5; a claim bitmap (1 bit/read); a chunked record log.
+// Data layout in HBM: reads[n][NW] u64 (NW = ceil(2L/64)); per dictionary the CSR (mixed keys, start, ids) in mixed-key
+// order and a 16-byte-slot open-addressing table ordered the same way, load factor <= 0.5; a claim bitmap (1 bit/read);
+// a chunked record log.
 #include "ctx.h"
 #include <utility>
 #include <algorithm>
