@@ -393,8 +393,9 @@ def main():
                                    if single_job else "1 independent read set per GPU"),
                    "l2": "inputs (%.1f GB ASCII, %.1f GB packed) exceed the 126 MB L2; no explicit flush" % ((n_clean + n_N) * 101 / 1e9, n_clean * 32 / 1e9)},
         "phases_ms": ph,
-        "stage1": {"matched": m, "singletons": s, "chain_heads": u, "probes_per_read": cnt["probes"] / max(1, cnt["steps"]),
-                   "compares_per_read": cnt["compares"] / max(1, cnt["steps"]), "claim_fails": cnt["claim_fails"]},
+        "stage1": {"matched": m, "singletons": s, "chain_heads": u, "probes_per_read": cnt["probes"] / max(1, n_clean),
+                   "compares_per_read": cnt["compares"] / max(1, n_clean), "claim_fails": cnt["claim_fails"],
+                   "search_rounds_from_shift_0": cnt["steps"], "harvested": cnt["harvested"]},
         "stage2": {"aligned_singletons": es.aligned_singletons, "aligned_N": es.aligned_N},
         "roofline": {"bound": "hbm", "kernel": "walk_kernel<4, 32> (one walker per warp)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,

@@ -52,7 +52,8 @@ class IngestInfo(ctypes.Structure):
 
 class Counters(ctypes.Structure):
     _fields_ = [("steps", ctypes.c_uint64), ("probes", ctypes.c_uint64), ("key_hits", ctypes.c_uint64),
-                ("compares", ctypes.c_uint64), ("claim_fails", ctypes.c_uint64), ("restarts", ctypes.c_uint64)]
+                ("compares", ctypes.c_uint64), ("claim_fails", ctypes.c_uint64), ("restarts", ctypes.c_uint64),
+                ("harvested", ctypes.c_uint64)]
 
 
 _lib = None

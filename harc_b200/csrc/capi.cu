@@ -437,7 +437,7 @@ int harcgpu_get_counters(harcgpu_ctx *c, harcgpu_counters *o)
 	CK(cudaSetDevice(c->device));
 	u64 v[8];
 	CK(cudaMemcpy(v, c->counters, 64, cudaMemcpyDeviceToHost));
-	o->steps = v[0]; o->probes = v[1]; o->key_hits = v[2]; o->compares = v[3]; o->claim_fails = v[4]; o->restarts = v[5];
+	o->steps = v[0]; o->probes = v[1]; o->key_hits = v[2]; o->compares = v[3]; o->claim_fails = v[4]; o->restarts = v[5]; o->harvested = v[6];
 	return 0;
 }
 

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 	if (sub < 2) { s.zpad2[sub] = 0u; s.zpad3[sub] = 0u; }
 	__syncthreads();
 
-	u32 c_steps = 0, c_probes = 0, c_hits = 0, c_cmp = 0, c_fail = 0, c_restart = 0;
+	u32 c_steps = 0, c_probes = 0, c_hits = 0, c_cmp = 0, c_fail = 0, c_restart = 0, c_harvest = 0;
 #ifdef WALK_PROF
 	u64 pacc[16];
 	for (int i = 0; i < 16; i++) pacc[i] = 0;
@@ -501,6 +501,21 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 			const u32 *hw = wbase + (off >> 5);
 			const int hr = off & 31;
 			const u32 *hm = mbase + j * W2;
+			// next entry of this lane's bin that is unclaimed and within the Hamming threshold (scanned from the tail)
+			auto advance = [&](const u32 *hw, int hr, const u32 *hm) { // window word, bit offset and mask row of the lane's shift
+				ps = P_DEAD;
+				while (left > 0 && seen < a.maxsearch) {
+					left--;
+					const u32 rid = size == 1 ? lo : __ldg(&ids_of(pc.key)[lo + left]);
+					const u32 cw = ldvol(peek_word(a, rid)); // claim bit and read are fetched together
+					load_read<NW>(a.reads, rid, rw);
+					if (!((cw >> (rid & 31)) & 1u)) continue; // removed from the bin in the reference (505-514)
+					seen++;
+					c_cmp++;
+					if (hamming<NW>(hw, hr, hm, rw) <= a.thresh) { cand = rid; ps = P_CAND; break; }
+				}
+			};
+			int k_win = 0;
 			while (true) {
 				if (ps == P_PENDING) {
 					const int r = bucket_step(pc.key, pc.s0, pc.s1, pc.home, lo, size);
@@ -514,19 +529,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 						pc.s1 = __ldg(&sl[pc.h + 1]);
 					}
 				}
-				if (ps == P_BIN) {
-					ps = P_DEAD;
-					while (left > 0 && seen < a.maxsearch) {
-						left--;
-						const u32 rid = size == 1 ? lo : __ldg(&ids_of(pc.key)[lo + left]);
-						const u32 cw = ldvol(peek_word(a, rid)); // claim bit and read are fetched together
-						load_read<NW>(a.reads, rid, rw);
-						if (!((cw >> (rid & 31)) & 1u)) continue; // removed from the bin in the reference (505-514)
-						seen++;
-						c_cmp++;
-						if (hamming<NW>(hw, hr, hm, rw) <= a.thresh) { cand = rid; ps = P_CAND; break; }
-					}
-				}
+				if (ps == P_BIN) advance(hw, hr, hm);
 				const u32 bc = __ballot_sync(gmask, ps == P_CAND) >> gbase, bp = __ballot_sync(gmask, ps == P_PENDING) >> gbase;
 				if (!(bc | bp)) break; // nothing matches in these shifts
 				if (bc && (!bp || (bc & (0u - bc)) < (bp & (0u - bp)))) {
@@ -539,6 +542,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 					got = __shfl_sync(gmask, got, gbase + win);
 					if (got) {
 						found = true;
+						k_win = win;
 						k_rid = __shfl_sync(gmask, cand, gbase + win);
 						k_j = jb + (win >> 2);
 						k_rev = (win & 3) >= 2;
@@ -555,26 +559,67 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 #endif
 			PROF_ADD(2);
 
-			if (found) {
-				// ---- a read was appended (reorder.cpp:560-578 / 624-641)
-				current = k_rid;
+			// ---- a read is appended (reorder.cpp:560-578 / 624-641); the lane that holds it has put it into s.cur
+			auto append = [&](u32 rid, int shift, int rv) {
+				current = rid;
 				__syncwarp(gmask);
-				update_ref<NW, G>(s, L, sub, gmask, false, k_rev != 0, k_j, head);
+				update_ref<NW, G>(s, L, sub, gmask, false, rv != 0, shift, head);
 				if (leader) {
 					if (!left_mode) {
 						if (prev_unmatched) emit(mkrec(prev, (u32)L, 0, 0, 0));
-						emit(mkrec(current, (u32)k_j, (u32)k_rev, 1, 0));
+						emit(mkrec(current, (u32)shift, (u32)rv, 1, 0));
 					} else {
 						// left run, found on the reverse-complement strand: in the final order this read precedes the one found
 						// before it, which therefore gets this shift; orientations flip
-						if (s.lcount == 0) s.j1 = (u32)k_j;
-						else lemit(mkrec(s.pend, (u32)k_j, s.pend_f ^ 1u, 1, 0));
+						if (s.lcount == 0) s.j1 = (u32)shift;
+						else lemit(mkrec(s.pend, (u32)shift, s.pend_f ^ 1u, 1, 0));
 						s.pend = current;
-						s.pend_f = (u32)k_rev;
+						s.pend_f = (u32)rv;
 						s.lcount++;
 					}
 				}
 				if (!left_mode) prev_unmatched = false;
+			};
+			if (found) {
+				append(k_rid, k_j, k_rev);
+				// Harvest (not in the reference; with `extend`, i.e. never with one walker): the lanes behind the winner have
+				// already fetched and Hamming-tested their candidates of this round.  Those up to the first lane that is not
+				// settled -- an unresolved bucket, or a bin with entries left (reads that start at the same position: the next
+				// round finds them at shift 0, with all lanes at work) -- claim their candidates in ONE wave (one claim per
+				// distinct read), and the claimed reads are appended in lane order = in order of their start positions, each
+				// with the difference of the shifts.  The probe round and the candidate fetches are paid once for all of them.
+				// (Draining the multi-entry bins inside the harvest was tried: it finds more reads per round, 1.55 against
+				// 1.0 extra, but its one-lane dependent loads make the walk slower, 31.7 ms against 24.5.)
+				if (a.extend != 0) {
+					const bool unsettled = sub >= k_win && (ps == P_PENDING || ps == P_BIN || ((ps == P_CAND || sub == k_win) && left > 0 && seen < a.maxsearch));
+					const u32 bu = __ballot_sync(gmask, unsettled) >> gbase;
+					int limit = G - 1; // last lane that may be harvested
+					if (bu) {
+						const int f = __ffs(bu) - 1;
+						const int fs = __shfl_sync(gmask, ps, gbase + f);
+						// an unsettled lane that holds a candidate may still give it; the winner's own bin ends everything
+						limit = f == k_win ? k_win : (fs == P_CAND ? f : f - 1);
+					}
+					const bool mine = sub > k_win && sub <= limit && ps == P_CAND && cand != k_rid;
+					const u32 grp = __match_any_sync(gmask, mine ? (u64)cand : ((1ull << 32) | (u64)lane)); // lanes that hold the same read
+					int got = 0;
+					if (mine && (__ffs(grp) - 1) == lane) { got = try_claim(a, cand); if (!got) c_fail++; }
+					u32 bh = __ballot_sync(gmask, got != 0) >> gbase;
+					int last_rel = k_win >> 2;
+					while (bh) {
+						const int w2 = __ffs(bh) - 1;
+						bh &= bh - 1;
+						const u32 rid2 = __shfl_sync(gmask, cand, gbase + w2);
+						__syncwarp(gmask);
+						if (sub == w2) {
+#pragma unroll
+							for (int k = 0; k < W2; k++) s.cur[k] = rw[k];
+						}
+						append(rid2, (w2 >> 2) - last_rel, (w2 & 3) >= 2);
+						last_rel = w2 >> 2;
+						c_harvest += leader;
+					}
+				}
 				dry = 0;
 				jb = 0;
 					PROF_CNT(10, 1);
@@ -653,10 +698,12 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 		c_cmp += __shfl_xor_sync(FULL, c_cmp, o);
 		c_fail += __shfl_xor_sync(FULL, c_fail, o);
 		c_restart += __shfl_xor_sync(FULL, c_restart, o);
+		c_harvest += __shfl_xor_sync(FULL, c_harvest, o);
 	}
 	if (lane == 0) {
 		atomicAdd(&a.counters[0], (u64)c_steps); atomicAdd(&a.counters[1], (u64)c_probes); atomicAdd(&a.counters[2], (u64)c_hits);
 		atomicAdd(&a.counters[3], (u64)c_cmp); atomicAdd(&a.counters[4], (u64)c_fail); atomicAdd(&a.counters[5], (u64)c_restart);
+		atomicAdd(&a.counters[6], (u64)c_harvest);
 	}
 }
 

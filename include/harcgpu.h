@@ -61,12 +61,13 @@ typedef struct {
 
 /* Device-side counters of the last stage I run (SURVEY §5 "metrics"). */
 typedef struct {
-	uint64_t steps;        /* chain steps taken (= reads visited) */
+	uint64_t steps;        /* search rounds that start at shift 0 (one per appended read unless reads are harvested) */
 	uint64_t probes;       /* dictionary probes issued */
 	uint64_t key_hits;     /* probes whose key was present */
 	uint64_t compares;     /* candidate reads fetched and Hamming-tested */
 	uint64_t claim_fails;  /* lost CAS claims */
 	uint64_t restarts;     /* chain heads picked (= the "unmatched" count of reorder.cpp:701) */
+	uint64_t harvested;    /* reads appended from the candidates a round had already fetched (not in the reference) */
 } harcgpu_counters;
 
 /* harc:52-63: fill p from the read length exactly as the CLI does. */
