@@ -581,6 +581,25 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 				if (!left_mode) prev_unmatched = false;
 			};
 			if (found) {
+				if (a.extend != 0) {
+					// for the harvest below: the lanes behind the winner whose bucket chain is still open finish it (their loads
+					// have been in flight since the winner was looked at) and test their candidates against this window
+					while (__any_sync(gmask, sub > k_win && (ps == P_PENDING || ps == P_BIN))) {
+						if (sub > k_win && ps == P_PENDING) {
+							const int r = bucket_step(pc.key, pc.s0, pc.s1, pc.home, lo, size);
+							if (r == 1) { ps = P_BIN; left = size; c_hits++; }
+							else if (r == 0) ps = P_DEAD;
+							else {
+								pc.home = false;
+								pc.h += 2;
+								const ulonglong2 *sl = slots_of(pc.key);
+								pc.s0 = __ldg(&sl[pc.h]);
+								pc.s1 = __ldg(&sl[pc.h + 1]);
+							}
+						}
+						if (sub > k_win && ps == P_BIN) advance(hw, hr, hm);
+					}
+				}
 				append(k_rid, k_j, k_rev);
 				// Harvest (not in the reference; with `extend`, i.e. never with one walker): the lanes behind the winner have
 				// already fetched and Hamming-tested their candidates of this round.  Those up to the first lane that is not
