@@ -130,7 +130,8 @@ __device__ __forceinline__ u32 lowmask32(int n) { return n >= 32 ? ~0u : (n <= 0
 // the low bits of the largest key.  The window is circular (origin `head`) over LP = 32*NW slots so that a shift
 // moves no data; slot p lives at index (p % B) * G + p / B, which makes the lanes touch G consecutive uint4.
 template <int NW, int G>
-__device__ __forceinline__ void update_ref(WalkerSmem<NW> &s, int L, int lane, u32 gmask, bool reset, bool rev, int shift, int &head)
+__device__ __forceinline__ void update_ref(WalkerSmem<NW> &s, int L, int lane, u32 gmask, bool reset, bool rev, int shift, int &head,
+                                           bool final = true)
 {
 	constexpr int B = 32 * NW / G, LP = 32 * NW, W2 = 2 * NW; // `lane` = lane inside the walker's group of G
 	if (reset) head = 0;
@@ -158,14 +159,16 @@ __device__ __forceinline__ void update_ref(WalkerSmem<NW> &s, int L, int lane, u
 		v.y += cc == 1u ? 4u : 0u;
 		v.z += cc == 2u ? 4u : 0u;
 		v.w += cc == 3u ? 4u : 0u;
+		s.key[idx] = v;
+		if (++r == B) { r = 0; q++; }
+		if (!final) continue; // more reads of this round follow: only the votes, the consensus is taken with the last one
 		u32 b = max(max(v.x, v.y), max(v.z, v.w));
 		// positions beyond the read (i >= L) live in slots that no valid position uses (LP >= L) and that are re-initialised
 		// when they enter the window, so the store needs no guard; their base is A, the zero bits of the reference's bitset
-		s.key[idx] = v;
 		if (i >= L) b = 3u;
 		out |= ((0x27u >> (2 * (b & 3u))) & 3u) << (2 * t); // tie rank 3,2,1,0 -> code A0 C2 G1 T3
-		if (++r == B) { r = 0; q++; }
 	}
+	if (!final) { __syncwarp(gmask); return; }
 	if ((2 * B) % 8 == 0) {
 		unsigned char *rb = reinterpret_cast<unsigned char *>(s.ref) + (2 * B / 8) * lane;
 		if (2 * B == 8) *rb = (unsigned char)out;
@@ -560,10 +563,10 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 			PROF_ADD(2);
 
 			// ---- a read is appended (reorder.cpp:560-578 / 624-641); the lane that holds it has put it into s.cur
-			auto append = [&](u32 rid, int shift, int rv) {
+			auto append = [&](u32 rid, int shift, int rv, bool last) { // last: no other read of this round follows
 				current = rid;
 				__syncwarp(gmask);
-				update_ref<NW, G>(s, L, sub, gmask, false, rv != 0, shift, head);
+				update_ref<NW, G>(s, L, sub, gmask, false, rv != 0, shift, head, last);
 				if (leader) {
 					if (!left_mode) {
 						if (prev_unmatched) emit(mkrec(prev, (u32)L, 0, 0, 0));
@@ -600,15 +603,16 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 						if (sub > k_win && ps == P_BIN) advance(hw, hr, hm);
 					}
 				}
-				append(k_rid, k_j, k_rev);
 				// Harvest (not in the reference; with `extend`, i.e. never with one walker): the lanes behind the winner have
 				// already fetched and Hamming-tested their candidates of this round.  Those up to the first lane that is not
-				// settled -- an unresolved bucket, or a bin with entries left (reads that start at the same position: the next
-				// round finds them at shift 0, with all lanes at work) -- claim their candidates in ONE wave (one claim per
-				// distinct read), and the claimed reads are appended in lane order = in order of their start positions, each
-				// with the difference of the shifts.  The probe round and the candidate fetches are paid once for all of them.
+				// settled -- a bin with entries left (reads that start at the same position: the next round finds them at
+				// shift 0, with all lanes at work) -- claim their candidates in ONE wave (one claim per distinct read), and the
+				// claimed reads are appended behind the winner in lane order = in order of their start positions, each with
+				// the difference of the shifts.  The probe round and the candidate fetches are paid once for all of them, and
+				// the consensus is only taken from the votes with the last read of the round.
 				// (Draining the multi-entry bins inside the harvest was tried: it finds more reads per round, 1.55 against
 				// 1.0 extra, but its one-lane dependent loads make the walk slower, 31.7 ms against 24.5.)
+				u32 bh = 0;
 				if (a.extend != 0) {
 					const bool unsettled = sub >= k_win && (ps == P_PENDING || ps == P_BIN || ((ps == P_CAND || sub == k_win) && left > 0 && seen < a.maxsearch));
 					const u32 bu = __ballot_sync(gmask, unsettled) >> gbase;
@@ -623,21 +627,22 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 					const u32 grp = __match_any_sync(gmask, mine ? (u64)cand : ((1ull << 32) | (u64)lane)); // lanes that hold the same read
 					int got = 0;
 					if (mine && (__ffs(grp) - 1) == lane) { got = try_claim(a, cand); if (!got) c_fail++; }
-					u32 bh = __ballot_sync(gmask, got != 0) >> gbase;
-					int last_rel = k_win >> 2;
-					while (bh) {
-						const int w2 = __ffs(bh) - 1;
-						bh &= bh - 1;
-						const u32 rid2 = __shfl_sync(gmask, cand, gbase + w2);
-						__syncwarp(gmask);
-						if (sub == w2) {
+					bh = __ballot_sync(gmask, got != 0) >> gbase;
+				}
+				append(k_rid, k_j, k_rev, bh == 0);
+				int last_rel = k_win >> 2;
+				while (bh) {
+					const int w2 = __ffs(bh) - 1;
+					bh &= bh - 1;
+					const u32 rid2 = __shfl_sync(gmask, cand, gbase + w2);
+					__syncwarp(gmask);
+					if (sub == w2) {
 #pragma unroll
-							for (int k = 0; k < W2; k++) s.cur[k] = rw[k];
-						}
-						append(rid2, (w2 >> 2) - last_rel, (w2 & 3) >= 2);
-						last_rel = w2 >> 2;
-						c_harvest += leader;
+						for (int k = 0; k < W2; k++) s.cur[k] = rw[k];
 					}
+					append(rid2, (w2 >> 2) - last_rel, (w2 & 3) >= 2, bh == 0);
+					last_rel = w2 >> 2;
+					c_harvest += leader;
 				}
 				dry = 0;
 				jb = 0;
