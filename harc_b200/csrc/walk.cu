@@ -620,8 +620,9 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 					if (bu) {
 						const int f = __ffs(bu) - 1;
 						const int fs = __shfl_sync(gmask, ps, gbase + f);
-						// an unsettled lane that holds a candidate may still give it; the winner's own bin ends everything
-						limit = f == k_win ? k_win : (fs == P_CAND ? f : f - 1);
+						// a lane whose bin has entries left ends the harvest behind its own shift: the lanes of the same shift
+						// (the other three probe kinds) may still give what they hold, the window then stops at that position
+						limit = (f == k_win || fs == P_CAND) ? (f | 3) : f - 1;
 					}
 					const bool mine = sub > k_win && sub <= limit && ps == P_CAND && cand != k_rid;
 					const u32 grp = __match_any_sync(gmask, mine ? (u64)cand : ((1ull << 32) | (u64)lane)); // lanes that hold the same read
