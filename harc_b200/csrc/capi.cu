@@ -2,6 +2,7 @@
 #include "ctx.h"
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <sys/stat.h>
 #include <string>
@@ -67,6 +68,8 @@ int harcgpu_create(int device, const harcgpu_params *p, harcgpu_ctx **out)
 	if (ndev <= 0) { harcgpu_set_error("no CUDA device: libharcgpu has no CPU fallback"); return -1; }
 	if (device < 0 || device >= ndev) { harcgpu_set_error("device %d out of range (%d devices)", device, ndev); return -1; }
 	CK(cudaSetDevice(device));
+	// tuning aids (profiles/): L2 fetch granularity for the random 32-byte bucket / read fetches of the walk
+	if (const char *e = getenv("HARCGPU_L2FETCH")) CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)));
 	harcgpu_ctx *c = new harcgpu_ctx();
 	c->device = device;
 	c->p = *p;

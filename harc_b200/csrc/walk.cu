@@ -18,6 +18,7 @@
 #include "ctx.h"
 #include <algorithm>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 constexpr int WALK_WARPS = 4;         // warps (= walkers) per block
@@ -519,42 +520,80 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 				}
 			};
 			int k_win = 0;
-			while (true) {
-				if (ps == P_PENDING) {
-					const int r = bucket_step(pc.key, pc.s0, pc.s1, pc.home, lo, size);
-					if (r == 1) { ps = P_BIN; left = size; c_hits++; }
-					else if (r == 0) ps = P_DEAD;
-					else {
-						pc.home = false;
-						pc.h += 2; // the table ends with two empty slots and never wraps
-						const ulonglong2 *sl = slots_of(pc.key);
-						pc.s0 = __ldg(&sl[pc.h]);
-						pc.s1 = __ldg(&sl[pc.h + 1]);
-					}
+			u32 bh = 0; // extend: lanes behind the first read of the round whose candidates were claimed in the same wave
+			// one step of a lane's bucket chain
+			auto resolve = [&]() {
+				const int r = bucket_step(pc.key, pc.s0, pc.s1, pc.home, lo, size);
+				if (r == 1) { ps = P_BIN; left = size; c_hits++; }
+				else if (r == 0) ps = P_DEAD;
+				else {
+					pc.home = false;
+					pc.h += 2; // the table ends with two empty slots and never wraps
+					const ulonglong2 *sl = slots_of(pc.key);
+					pc.s0 = __ldg(&sl[pc.h]);
+					pc.s1 = __ldg(&sl[pc.h + 1]);
 				}
+			};
+			while (true) {
+				if (ps == P_PENDING) resolve();
 				if (ps == P_BIN) advance(hw, hr, hm);
 				const u32 bc = __ballot_sync(gmask, ps == P_CAND) >> gbase, bp = __ballot_sync(gmask, ps == P_PENDING) >> gbase;
 				if (!(bc | bp)) break; // nothing matches in these shifts
-				if (bc && (!bp || (bc & (0u - bc)) < (bp & (0u - bp)))) {
-					const int win = __ffs(bc) - 1;
+				if (!(bc && (!bp || (bc & (0u - bc)) < (bp & (0u - bp))))) continue;
+				const int win = __ffs(bc) - 1;
+				if (a.extend == 0) {
+					// the reference's walk (reorder.cpp:545-556): the first candidate in sequential order is claimed
 					int got = 0;
 					if (sub == win) {
 						got = try_claim(a, cand);
 						if (!got) { c_fail++; ps = P_BIN; }
 					}
 					got = __shfl_sync(gmask, got, gbase + win);
-					if (got) {
-						found = true;
-						k_win = win;
-						k_rid = __shfl_sync(gmask, cand, gbase + win);
-						k_j = jb + (win >> 2);
-						k_rev = (win & 3) >= 2;
-						if (sub == win) {
+					if (!got) continue;
+					found = true;
+					k_win = win;
+					break;
+				}
+				// Harvest (not in the reference; with `extend`, i.e. never with one walker): the lanes behind the winner have
+				// already fetched their buckets of this round -- reads that start a few positions further on, which the next
+				// rounds would find again one by one.  They first finish their open bucket chains and test their candidates
+				// against this window; then the winner and the lanes behind it, up to the first lane that is not settled -- a
+				// bin with entries left (reads that start at the same position: the next round finds them at shift 0, with all
+				// lanes at work) -- claim their candidates in ONE wave of atomics (one claim per distinct read).  The claimed
+				// reads are appended in lane order = in order of their start positions, each with the difference of the
+				// shifts.  The probe round, the candidate fetches and the claim round trip (over NVLink when the read's bitmap
+				// range lives on another GPU) are paid once for all of them.
+				// (Draining the multi-entry bins inside the harvest was tried: it finds more reads per round, 1.55 against
+				// 1.0 extra, but its one-lane dependent loads make the walk slower, 31.7 ms against 24.5.)
+				while (__any_sync(gmask, sub > win && (ps == P_PENDING || ps == P_BIN))) {
+					if (sub > win && ps == P_PENDING) resolve();
+					if (sub > win && ps == P_BIN) advance(hw, hr, hm);
+				}
+				const bool unsettled = sub >= win && ps == P_CAND && left > 0 && seen < a.maxsearch;
+				const u32 bu = __ballot_sync(gmask, unsettled) >> gbase;
+				// a lane whose bin has entries left ends the harvest behind its own shift: the lanes of the same shift (the
+				// other three probe kinds) may still give what they hold, the window then stops at that position
+				const int limit = bu ? ((__ffs(bu) - 1) | 3) : G - 1;
+				const bool mine = sub >= win && sub <= limit && ps == P_CAND;
+				const u32 grp = __match_any_sync(gmask, mine ? (u64)cand : ((1ull << 32) | (u64)lane)); // lanes that hold the same read
+				const bool first_of_grp = mine && (__ffs(grp) - 1) == lane;
+				int got = 0;
+				if (first_of_grp) { got = try_claim(a, cand); if (!got) c_fail++; }
+				bh = __ballot_sync(gmask, got != 0) >> gbase;
+				if (mine && !got) ps = P_BIN; // lost (or the same read as a lane in front): on with the bin if the round goes on
+				if (!bh) continue;            // every claim of the wave was lost to other walkers
+				found = true;
+				k_win = __ffs(bh) - 1;
+				bh &= bh - 1;
+				break;
+			}
+			if (found) {
+				k_rid = __shfl_sync(gmask, cand, gbase + k_win);
+				k_j = jb + (k_win >> 2);
+				k_rev = (k_win & 3) >= 2;
+				if (sub == k_win) {
 #pragma unroll
-							for (int k = 0; k < W2; k++) s.cur[k] = rw[k];
-						}
-						break;
-					}
+					for (int k = 0; k < W2; k++) s.cur[k] = rw[k];
 				}
 			}
 #ifdef WALK_PROF
@@ -584,52 +623,6 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 				if (!left_mode) prev_unmatched = false;
 			};
 			if (found) {
-				if (a.extend != 0) {
-					// for the harvest below: the lanes behind the winner whose bucket chain is still open finish it (their loads
-					// have been in flight since the winner was looked at) and test their candidates against this window
-					while (__any_sync(gmask, sub > k_win && (ps == P_PENDING || ps == P_BIN))) {
-						if (sub > k_win && ps == P_PENDING) {
-							const int r = bucket_step(pc.key, pc.s0, pc.s1, pc.home, lo, size);
-							if (r == 1) { ps = P_BIN; left = size; c_hits++; }
-							else if (r == 0) ps = P_DEAD;
-							else {
-								pc.home = false;
-								pc.h += 2;
-								const ulonglong2 *sl = slots_of(pc.key);
-								pc.s0 = __ldg(&sl[pc.h]);
-								pc.s1 = __ldg(&sl[pc.h + 1]);
-							}
-						}
-						if (sub > k_win && ps == P_BIN) advance(hw, hr, hm);
-					}
-				}
-				// Harvest (not in the reference; with `extend`, i.e. never with one walker): the lanes behind the winner have
-				// already fetched and Hamming-tested their candidates of this round.  Those up to the first lane that is not
-				// settled -- a bin with entries left (reads that start at the same position: the next round finds them at
-				// shift 0, with all lanes at work) -- claim their candidates in ONE wave (one claim per distinct read), and the
-				// claimed reads are appended behind the winner in lane order = in order of their start positions, each with
-				// the difference of the shifts.  The probe round and the candidate fetches are paid once for all of them, and
-				// the consensus is only taken from the votes with the last read of the round.
-				// (Draining the multi-entry bins inside the harvest was tried: it finds more reads per round, 1.55 against
-				// 1.0 extra, but its one-lane dependent loads make the walk slower, 31.7 ms against 24.5.)
-				u32 bh = 0;
-				if (a.extend != 0) {
-					const bool unsettled = sub >= k_win && (ps == P_PENDING || ps == P_BIN || ((ps == P_CAND || sub == k_win) && left > 0 && seen < a.maxsearch));
-					const u32 bu = __ballot_sync(gmask, unsettled) >> gbase;
-					int limit = G - 1; // last lane that may be harvested
-					if (bu) {
-						const int f = __ffs(bu) - 1;
-						const int fs = __shfl_sync(gmask, ps, gbase + f);
-						// a lane whose bin has entries left ends the harvest behind its own shift: the lanes of the same shift
-						// (the other three probe kinds) may still give what they hold, the window then stops at that position
-						limit = (f == k_win || fs == P_CAND) ? (f | 3) : f - 1;
-					}
-					const bool mine = sub > k_win && sub <= limit && ps == P_CAND && cand != k_rid;
-					const u32 grp = __match_any_sync(gmask, mine ? (u64)cand : ((1ull << 32) | (u64)lane)); // lanes that hold the same read
-					int got = 0;
-					if (mine && (__ffs(grp) - 1) == lane) { got = try_claim(a, cand); if (!got) c_fail++; }
-					bh = __ballot_sync(gmask, got != 0) >> gbase;
-				}
 				append(k_rid, k_j, k_rev, bh == 0);
 				int last_rel = k_win >> 2;
 				while (bh) {
@@ -927,10 +920,35 @@ int s1_reorder(harcgpu_ctx *c)
 	a.recs = recs; a.chunk_key = chunk_key; a.chunk_fill = chunk_fill; a.chunk_ctr = ctrs; a.max_chunks = max_chunks;
 	a.lrecs = lrecs; a.lprev = lprev; a.lchunk_ctr = ctrs + 1; a.max_lchunks = max_chunks;
 	a.counters = c->counters;
+	// tuning aid: keep the claim bitmap (1 bit per read, hit by every candidate test and claim) in the persisting part of L2
+	bool l2win = false;
+	if (const char *e = getenv("HARCGPU_L2PERSIST")) {
+		const size_t want = ((size_t)n + 31) / 32 * 4;
+		int maxwin = 0;
+		CK(cudaDeviceGetAttribute(&maxwin, cudaDevAttrMaxAccessPolicyWindowSize, c->device));
+		if (atoi(e) > 0 && !sharded && want <= (size_t)maxwin) {
+			CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(want * 2, (size_t)atoi(e) << 20)));
+			cudaStreamAttrValue av;
+			memset(&av, 0, sizeof av);
+			av.accessPolicyWindow.base_ptr = c->claim;
+			av.accessPolicyWindow.num_bytes = want;
+			av.accessPolicyWindow.hitRatio = 1.0f;
+			av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+			av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+			CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
+			l2win = true;
+		}
+	}
 	c->tic();
 	DISPATCH_NW_G(c->NW, lanes, (rc = launch_walk<NW, G>(c, a)));
 	if (rc) return rc;
 	c->toc("walk");
+	if (l2win) {
+		cudaStreamAttrValue av;
+		memset(&av, 0, sizeof av);
+		CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
+		CK(cudaCtxResetPersistingL2Cache());
+	}
 	CK(cudaGetLastError());
 #ifdef WALK_PROF
 	{
