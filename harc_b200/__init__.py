@@ -19,7 +19,8 @@ EXPORTS = [
     "harcgpu_set_stream", "harcgpu_load_pool", "harcgpu_encode", "harcgpu_get_encode_sizes", "harcgpu_get_set_sizes",
     "harcgpu_get_set", "harcgpu_get_globals", "harcgpu_reorder_dir", "harcgpu_encode_dir", "harcgpu_last_ms", "harcgpu_stream",
     "harcgpu_load_pool_device", "harcgpu_launch_count", "harcgpu_stage_nreads",
-    "harcgpu_shard_init", "harcgpu_shard_connect", "harcgpu_shard_reset", "harcgpu_set_pool_exchange", "harcgpu_load_pool_ids",
+    "harcgpu_job_init", "harcgpu_job_connect", "harcgpu_job_load_reads", "harcgpu_job_load_reads_device", "harcgpu_job_build_dicts",
+    "harcgpu_job_reorder", "harcgpu_job_set_barrier", "harcgpu_set_pool_exchange", "harcgpu_load_pool_ids", "harcgpu_device_result",
     "harcgpu_get_packed_order",
     "harcgpu_debug_sort", "harcgpu_fastq_readlen", "harcgpu_ingest_fastq", "harcgpu_ingest_fastq_device", "harcgpu_get_ingest", "harcgpu_load_pool_ingested",
 ]
@@ -59,6 +60,7 @@ class Counters(ctypes.Structure):
 _lib = None
 # hook of harcgpu_set_pool_exchange: int fn(void *user, void *d_best, uint64_t count)
 POOL_EXCHANGE = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64)
+JOB_BARRIER = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p)
 
 
 def load_library():
@@ -92,9 +94,14 @@ def load_library():
     lib.harcgpu_encode.argtypes = [vp]
     lib.harcgpu_load_pool_device.argtypes = [vp, vp, u32]
     lib.harcgpu_stage_nreads.argtypes = [vp, vp, u32]
-    lib.harcgpu_shard_init.argtypes = [vp, ctypes.c_int, ctypes.c_int, u32, vp]
-    lib.harcgpu_shard_connect.argtypes = [vp, vp]
-    lib.harcgpu_shard_reset.argtypes = [vp]
+    lib.harcgpu_job_init.argtypes = [vp, ctypes.c_int, ctypes.c_int, u32, u32, u32, vp, ctypes.POINTER(vp)]
+    lib.harcgpu_job_connect.argtypes = [vp, vp, ctypes.POINTER(vp)]
+    lib.harcgpu_job_set_barrier.argtypes = [vp, JOB_BARRIER, vp]
+    lib.harcgpu_job_load_reads.argtypes = [vp, vp, u32]
+    lib.harcgpu_job_load_reads_device.argtypes = [vp, vp, u32]
+    lib.harcgpu_job_build_dicts.argtypes = [vp]
+    lib.harcgpu_job_reorder.argtypes = [vp]
+    lib.harcgpu_device_result.argtypes = [vp, cp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_uint64)]
     lib.harcgpu_set_pool_exchange.argtypes = [vp, POOL_EXCHANGE, vp]
     lib.harcgpu_load_pool_ids.argtypes = [vp, vp, u32, vp, u32]
     lib.harcgpu_get_packed_order.argtypes = [vp, vp, vp, vp, vp]
@@ -166,6 +173,10 @@ class HarcGpu:
         h = ctypes.c_void_p()
         self._ck(self.lib.harcgpu_create(device, ctypes.byref(self.p), ctypes.byref(h)))
         self.h = h
+
+    def NW(self):
+        """64-bit words of a packed read."""
+        return (2 * self.L + 63) // 64
 
     def _ck(self, rc):
         if rc != 0:
@@ -298,17 +309,46 @@ class HarcGpu:
         self._ck(self.lib.harcgpu_stage_nreads(self.h, _ptr(N_ascii), len(N_ascii) // (self.L + 1)))
 
     # ---- one job on several GPUs (see harc_b200/multi.py for the driver)
-    def shard_init(self, rank, world, n_total):
+    def job_init(self, rank, world, n_total, base, n_local):
+        """Returns (CUDA IPC handle of this GPU's arena, its device pointer)."""
         h = ctypes.create_string_buffer(64)
-        self._ck(self.lib.harcgpu_shard_init(self.h, rank, world, n_total, ctypes.cast(h, ctypes.c_void_p)))
-        return h.raw
+        p = ctypes.c_void_p()
+        self._ck(self.lib.harcgpu_job_init(self.h, rank, world, n_total, base, n_local, ctypes.cast(h, ctypes.c_void_p), ctypes.byref(p)))
+        return h.raw, int(p.value)
 
-    def shard_connect(self, handles):
-        buf = ctypes.create_string_buffer(b"".join(handles), 64 * len(handles))
-        self._ck(self.lib.harcgpu_shard_connect(self.h, ctypes.cast(buf, ctypes.c_void_p)))
+    def job_connect(self, handles=None, local_ptrs=None):
+        """handles: the 64-byte IPC handles of all ranks (other processes); local_ptrs: the arenas of contexts of this process."""
+        if local_ptrs is not None:
+            arr = (ctypes.c_void_p * len(local_ptrs))(*[ctypes.c_void_p(int(q)) for q in local_ptrs])
+            self._ck(self.lib.harcgpu_job_connect(self.h, None, arr))
+        else:
+            buf = ctypes.create_string_buffer(b"".join(handles), 64 * len(handles))
+            self._ck(self.lib.harcgpu_job_connect(self.h, ctypes.cast(buf, ctypes.c_void_p), None))
 
-    def shard_reset(self):
-        self._ck(self.lib.harcgpu_shard_reset(self.h))
+    def job_set_barrier(self, fn):
+        """fn() -> None: host barrier over the ranks of the job (ranks that share one GPU; see harcgpu.h)."""
+        def tramp(user):
+            try:
+                fn()
+                return 0
+            except Exception:
+                return -1
+        self._bar_hook = JOB_BARRIER(tramp)
+        self._ck(self.lib.harcgpu_job_set_barrier(self.h, self._bar_hook, None))
+
+    def job_load_reads(self, ascii_lines, n_local):
+        a = np.frombuffer(ascii_lines, dtype=np.uint8) if isinstance(ascii_lines, (bytes, bytearray)) else ascii_lines
+        self._keep = a
+        self._ck(self.lib.harcgpu_job_load_reads(self.h, _ptr(a) if n_local else None, n_local))
+
+    def job_load_reads_device(self, dptr, n_local):
+        self._ck(self.lib.harcgpu_job_load_reads_device(self.h, ctypes.c_void_p(dptr), n_local))
+
+    def device_result(self, name):
+        """(device pointer, element count) of a result kept on the GPU: 'singleton_ids', 'order', 'out_order'."""
+        p, n = ctypes.c_void_p(), ctypes.c_uint64()
+        self._ck(self.lib.harcgpu_device_result(self.h, name.encode(), ctypes.byref(p), ctypes.byref(n)))
+        return int(p.value or 0), int(n.value)
 
     def set_pool_exchange(self, fn):
         """fn(device_pointer, count) -> None must min-reduce the int64 array over all ranks (None removes the hook)."""
@@ -326,13 +366,18 @@ class HarcGpu:
             self._hook = POOL_EXCHANGE(tramp)
         self._ck(self.lib.harcgpu_set_pool_exchange(self.h, self._hook, None))
 
-    def load_pool_ids(self, singleton_ids, N_ascii=None, n_N=None):
-        """N_ascii: uint8 array, or a raw pointer (int; host or device memory) together with n_N."""
-        ids = np.ascontiguousarray(singleton_ids, dtype=np.uint32)
+    def load_pool_ids(self, singleton_ids, N_ascii=None, n_N=None, n_s=None):
+        """singleton_ids: uint32 array, or a raw pointer (int; host or device memory) together with n_s; N_ascii: uint8
+        array, or a raw pointer together with n_N."""
+        if isinstance(singleton_ids, int) or singleton_ids is None:
+            ids, n_s = singleton_ids, int(n_s or 0)
+        else:
+            ids = np.ascontiguousarray(singleton_ids, dtype=np.uint32)
+            n_s = len(ids)
         if n_N is None:
             n_N = 0 if N_ascii is None else len(N_ascii) // (self.L + 1)
         self._keep3 = (ids, N_ascii)
-        self._ck(self.lib.harcgpu_load_pool_ids(self.h, _ptr(ids), len(ids), _ptr(N_ascii), n_N))
+        self._ck(self.lib.harcgpu_load_pool_ids(self.h, _ptr(ids) if n_s else None, n_s, _ptr(N_ascii) if n_N else None, n_N))
 
     def load_pool_device(self, dptr, n_N):
         self._ck(self.lib.harcgpu_load_pool_device(self.h, ctypes.c_void_p(dptr), n_N))

@@ -10,7 +10,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr",
            "-ccbin", "/usr/bin/g++"] + os.environ.get("HARC_CUFLAGS", "").split()
-CU = ["capi.cu", "stage1.cu", "walk.cu", "stage2.cu", "scan.cu", "ingest.cu", "sort.cu"]
+CU = ["capi.cu", "stage1.cu", "walk.cu", "stage2.cu", "scan.cu", "ingest.cu", "sort.cu", "job.cu"]
 HDR = ["common.cuh", "ctx.h", os.path.join("..", "..", "include", "harcgpu.h")]
 EXES = {"reorder.out": "reorder_main.cpp", "encoder.out": "encoder_main.cpp"}
 

@@ -19,7 +19,6 @@ void harcgpu_set_error(const char *fmt, ...)
 }
 
 extern "C" {
-static void shard_close(harcgpu_ctx *c);
 
 const char *harcgpu_last_error(void) { return g_err; }
 uint64_t harcgpu_launch_count(void) { return g_harcgpu_launches; }
@@ -92,12 +91,13 @@ void harcgpu_destroy(harcgpu_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->st);
-	shard_close(c);
+	job_close(c);
 	if (c->st_copy) { cudaStreamSynchronize(c->st_copy); cudaStreamDestroy(c->st_copy); cudaEventDestroy(c->ev_staged); cudaEventDestroy(c->ev_order); }
 	for (auto &b : c->live) cudaFree(b.p);
 	c->trim();
 	cudaEventDestroy(c->ev0);
 	cudaEventDestroy(c->ev1);
+	if (c->evl0) { cudaEventDestroy(c->evl0); cudaEventDestroy(c->evl1); }
 	cudaStreamDestroy(c->st);
 	delete c;
 }
@@ -110,16 +110,20 @@ double harcgpu_last_ms(harcgpu_ctx *c, const char *phase)
 	if (!strcmp(phase, "cudaMalloc_calls")) return (double)c->n_cuda_malloc;
 	if (!strcmp(phase, "cached_MB")) return (double)c->cached_bytes / 1048576.0;
 	if (!strcmp(phase, "peak_MB")) return (double)c->peak_bytes / 1048576.0;
+	if (!strcmp(phase, "job_bloom_bytes")) return c->dicts_sharded ? (double)(c->shard_world - 1) * c->bloom_seg_words * 4.0 : 0.0;
+	if (!strcmp(phase, "walkers")) return (double)c->walkers_used;
 	auto it = c->ms.find(phase);
 	return it == c->ms.end() ? -1.0 : it->second;
 }
 
 static int reset_stage1(harcgpu_ctx *c, u32 n)
 {
+	if (c->arena[c->shard_rank]) job_close(c); // the context leaves a job on several GPUs: its reads lived in the arena
 	c->release(c->reads); c->release(c->claim);
 	c->reads = nullptr; c->claim = nullptr;
 	for (int l = 0; l < 2; l++) free_dict(c, c->d1[l]);
-	c->dicts_built = false; c->reordered = false;
+	// everything derived from the reads of before is stale now, stage II inputs and outputs included
+	c->dicts_built = false; c->reordered = false; c->stream_set = false; c->pool_set = false; c->encoded = false;
 	c->n = n;
 	if (c->alloc(&c->reads, (size_t)n * c->NW) || c->alloc(&c->claim, ((size_t)n + 31) / 32)) return -1;
 	return 0;
@@ -128,6 +132,7 @@ static int reset_stage1(harcgpu_ctx *c, u32 n)
 int harcgpu_load_reads_device(harcgpu_ctx *c, const void *d_ascii, u32 n)
 {
 	if (!c || (!d_ascii && n)) { harcgpu_set_error("null argument"); return -1; }
+	if ((uintptr_t)d_ascii & 15) { harcgpu_set_error("harcgpu_load_reads_device: the buffer must be 16-byte aligned"); return -1; }
 	CK(cudaSetDevice(c->device));
 	if (reset_stage1(c, n)) return -1;
 	c->tic();
@@ -167,8 +172,9 @@ int harcgpu_ingest_fastq_device(harcgpu_ctx *c, const void *d_fastq, uint64_t nb
 {
 	if (!c || (!d_fastq && nbytes)) { harcgpu_set_error("null argument"); return -1; }
 	CK(cudaSetDevice(c->device));
+	if (c->arena[c->shard_rank]) job_close(c);
 	for (int l = 0; l < 2; l++) free_dict(c, c->d1[l]);
-	c->dicts_built = false; c->reordered = false;
+	c->dicts_built = false; c->reordered = false; c->stream_set = false; c->pool_set = false; c->encoded = false;
 	u64 total = 0;
 	u32 nc = 0, nn = 0;
 	if (ing_ingest(c, (const char *)d_fastq, nbytes, &total, &nc, &nn)) return -1;
@@ -221,19 +227,10 @@ int harcgpu_build_dicts(harcgpu_ctx *c)
 {
 	if (!c || !c->reads) { harcgpu_set_error("load reads first"); return -1; }
 	CK(cudaSetDevice(c->device));
+	if (c->shard_world > 1) return harcgpu_job_build_dicts(c);
 	c->tic();
-	if (c->dicts_sharded && c->shard_n != c->n) { harcgpu_set_error("sharded dictionaries: harcgpu_shard_init was called for %u reads, %u are loaded", c->shard_n, c->n); return -1; }
-	for (int l = 0; l < c->p.numdict; l++) {
-		DictShard sh;
-		if (c->dicts_sharded) {
-			char *arena = (char *)c->seg[c->shard_rank];
-			sh.rank = c->shard_rank; sh.world = c->shard_world; sh.cap = c->shard_cap; sh.nslots = c->shard_nslots;
-			sh.slots = (ulonglong2 *)(arena + c->arena_slots_off[l]);
-			sh.ids = (u32 *)(arena + c->arena_ids_off[l]);
-		}
-		if (build_dict(c, c->d1[l], c->reads, nullptr, c->n, c->NW, c->p.dict_start[l], c->p.dict_end[l], 2, c->dicts_sharded ? &sh : nullptr))
-			return -1;
-	}
+	for (int l = 0; l < c->p.numdict; l++)
+		if (build_dict(c, c->d1[l], c->reads, nullptr, c->n, c->NW, c->p.dict_start[l], c->p.dict_end[l], 2, nullptr)) return -1;
 	c->toc("dict");
 	c->dicts_built = true;
 	return 0;
@@ -296,95 +293,8 @@ int harcgpu_reorder(harcgpu_ctx *c)
 	if (!c || !c->reads) { harcgpu_set_error("load reads first"); return -1; }
 	CK(cudaSetDevice(c->device));
 	if (!c->dicts_built && harcgpu_build_dicts(c)) return -1;
+	if (c->shard_world > 1) return harcgpu_job_reorder(c);
 	return s1_reorder(c);
-}
-
-// ---- one job on several GPUs -------------------------------------------------------------------------------
-static void shard_close(harcgpu_ctx *c)
-{
-	for (int r = 0; r < 8; r++) {
-		if (c->seg[r] && c->seg_opened[r]) cudaIpcCloseMemHandle(c->seg[r]);
-		else if (c->seg[r]) c->release(c->seg[r]);
-		c->seg[r] = nullptr; c->seg_opened[r] = false;
-	}
-	c->shard_world = 1; c->shard_rank = 0; c->shard_n = 0; c->seg_per = 0; c->shard_ready = false;
-	if (c->dicts_sharded) {
-		for (int l = 0; l < 2; l++) free_dict(c, c->d1[l]); // their slots / ids pointed into the arena
-		c->dicts_built = false;
-	}
-	c->dicts_sharded = false; c->shard_cap = 0;
-}
-
-int harcgpu_shard_init(harcgpu_ctx *c, int rank, int world, uint32_t n_total, void *ipc_handle_out)
-{
-	if (!c || !ipc_handle_out || world < 1 || world > 8 || rank < 0 || rank >= world) { harcgpu_set_error("bad shard arguments (1..8 GPUs)"); return -1; }
-	CK(cudaSetDevice(c->device));
-	CK(cudaStreamSynchronize(c->st));
-	shard_close(c);
-	c->shard_rank = rank; c->shard_world = world; c->shard_n = n_total;
-	c->seg_per = (uint32_t)((((uint64_t)n_total + world - 1) / world + 31) / 32 * 32);
-	if (c->seg_per == 0) c->seg_per = 32;
-	// arena of this GPU: its bitmap range, then per dictionary its shard of the key table and room for its id lists
-	auto round256 = [](size_t b) { return (b + 255) / 256 * 256; };
-	size_t off = round256((size_t)c->seg_per / 8);
-	c->dicts_sharded = c->p.shard_dicts != 0 && world > 1;
-	if (c->dicts_sharded) {
-		const u64 per = ((u64)n_total + world - 1) / world;
-		u64 cap = 16;
-		while (cap < 2 * per + per / 4 + 1024) cap <<= 1; // load factor <= 0.45 even for a shard 10 % above the mean
-		if (cap > 0x80000000ull) { harcgpu_set_error("dictionary shard too large"); return -1; }
-		c->shard_cap = (u32)cap;
-		c->shard_nslots = cap + cap / 8 + 1024;
-		for (int l = 0; l < c->p.numdict; l++) {
-			c->arena_slots_off[l] = off; off += (size_t)c->shard_nslots * sizeof(ulonglong2);
-			c->arena_ids_off[l] = off;   off += round256((size_t)n_total * 4); // worst case: every read in one shard
-		}
-		for (int l = 0; l < 2; l++) free_dict(c, c->d1[l]);
-		c->dicts_built = false;
-	}
-	char *arena = nullptr;
-	if (c->alloc(&arena, off)) return -1;
-	c->seg[rank] = (u32 *)arena;
-	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-	cudaIpcMemHandle_t h;
-	CK(cudaIpcGetMemHandle(&h, c->seg[rank]));
-	memcpy(ipc_handle_out, &h, sizeof h);
-	return 0;
-}
-
-int harcgpu_shard_connect(harcgpu_ctx *c, const void *handles)
-{
-	if (!c || !handles || c->shard_world < 1 || !c->seg[c->shard_rank]) { harcgpu_set_error("harcgpu_shard_init first"); return -1; }
-	CK(cudaSetDevice(c->device));
-	for (int r = 0; r < c->shard_world; r++) {
-		if (r == c->shard_rank) continue;
-		cudaIpcMemHandle_t h;
-		memcpy(&h, (const char *)handles + 64 * (size_t)r, sizeof h);
-		void *p = nullptr;
-		CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-		c->seg[r] = (u32 *)p;
-		c->seg_opened[r] = true;
-	}
-	return 0;
-}
-
-int harcgpu_shard_reset(harcgpu_ctx *c)
-{
-	if (!c || c->shard_world < 2 || !c->seg[c->shard_rank]) { harcgpu_set_error("not a sharded context"); return -1; }
-	CK(cudaSetDevice(c->device));
-	const u64 lo = std::min<u64>((u64)c->shard_rank * c->seg_per, c->shard_n), hi = std::min<u64>(lo + c->seg_per, c->shard_n);
-	CK(cudaMemsetAsync(c->seg[c->shard_rank], 0, (size_t)c->seg_per / 8, c->st));
-	if (s1_init_claim(c, c->seg[c->shard_rank], (u32)(hi - lo))) return -1;
-	CK(cudaStreamSynchronize(c->st));
-	c->shard_ready = true;
-	return 0;
-}
-
-int harcgpu_set_pool_exchange(harcgpu_ctx *c, int (*fn)(void *, void *, uint64_t), void *user)
-{
-	if (!c) { harcgpu_set_error("null argument"); return -1; }
-	c->pool_exchange = fn; c->pool_exchange_user = user;
-	return 0;
 }
 
 int harcgpu_reorder_counts(harcgpu_ctx *c, uint32_t *nm, uint32_t *ns, uint32_t *nu)
@@ -431,6 +341,22 @@ int harcgpu_get_reordered_reads(harcgpu_ctx *c, char *temp_dna, char *temp_dna_s
 		CK(cudaStreamSynchronize(c->st));
 		c->release(d);
 	}
+	return 0;
+}
+
+int harcgpu_device_result(harcgpu_ctx *c, const char *name, const void **ptr, uint64_t *count)
+{
+	if (!c || !name || !ptr || !count) { harcgpu_set_error("null argument"); return -1; }
+	if (!strcmp(name, "singleton_ids")) {
+		if (!c->reordered) { harcgpu_set_error("reorder first"); return -1; }
+		*ptr = c->order_s; *count = c->n_single;
+	} else if (!strcmp(name, "order")) {
+		if (!c->reordered) { harcgpu_set_error("reorder first"); return -1; }
+		*ptr = c->order; *count = c->n_matched;
+	} else if (!strcmp(name, "out_order")) {
+		if (!c->encoded) { harcgpu_set_error("encode first"); return -1; }
+		*ptr = c->o_order; *count = c->esz.n_order;
+	} else { harcgpu_set_error("unknown device result '%s'", name); return -1; }
 	return 0;
 }
 

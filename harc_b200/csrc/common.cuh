@@ -68,6 +68,16 @@ __device__ __forceinline__ u32 mix_shard(u64 t, int world) { return (u32)__umul6
 // home bucket (even slot) of mixed key t in a table of 2^(64 - shift) nominal slots
 __device__ __forceinline__ u32 slot_home(u64 t, int shift, int world) { return (u32)((world > 1 ? t * (u64)world : t) >> shift) & ~1u; }
 
+// One job on several GPUs: blocked Bloom filter over the keys of all shards of both dictionaries, one segment per shard
+// (built by the shard's owner, copied to every GPU): word and the two bits of mixed key t of dictionary l.
+__device__ __forceinline__ void job_bloom_pos(u64 t, int l, int world, u32 seg_words, u32 &word, u32 &bits)
+{
+	u64 h = (t ^ (l ? 0x9E3779B97F4A7C15ull : 0ull)) * 0xD6E8FEB86659FD93ull;
+	h ^= h >> 32;
+	word = mix_shard(t, world) * seg_words + ((u32)(h >> 10) & (seg_words - 1u));
+	bits = (1u << ((u32)h & 31u)) | (1u << (((u32)h >> 5) & 31u));
+}
+
 // One dictionary: CSR over the bins in mixed-key order (ids ascending inside a bin: reorder.cpp:344-391) plus the
 // open-addressing table mixed key -> bin.  A slot is 16 bytes {mixed key, val}: val == 0 = empty, else size = bits 32..62
 // and the low half is the bin's first index into ids[] -- or, for a bin of one read (most bins), the read id itself, so

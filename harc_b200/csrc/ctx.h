@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include <map>
+#include <stdlib.h>
 #include <vector>
 
 struct DevBuf {
@@ -34,21 +35,32 @@ struct harcgpu_ctx {
 	long long *gpos = nullptr;
 	u64 *counters = nullptr; // 8 x u64
 	u32 walkers_used = 0;
-	// one job on several GPUs (harcgpu_shard_*): claim bitmap cut into contiguous id ranges, one per GPU
+	// ---- one job on several GPUs (job.cu, harcgpu_job_*).  Every GPU owns one allocation, its ARENA, which the other GPUs
+	// map (CUDA IPC between processes; plain pointers between contexts of one process): a header (barrier flags, the
+	// counts of the key exchange), its range of the claim bitmap, a full replica of the packed reads (every GPU packs its
+	// slice of the input and stores the result into all replicas), per dictionary the receive buffers of the key
+	// exchange, its shard of the key table and of the id lists, and its copy of the Bloom filter over all shards.
 	int shard_rank = 0, shard_world = 1;
-	u32 shard_n = 0, seg_per = 0;
-	// One allocation per GPU ("arena": its bitmap range, then per dictionary its shard of the key table and of the id
-	// lists), so that one IPC handle per GPU is exchanged; seg[r] = bitmap range of GPU r = start of arena r.
-	u32 *seg[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // seg[shard_rank] is local
+	u32 shard_n = 0, seg_per = 0;         // reads of the whole job; reads per bitmap range
+	u32 job_base = 0, job_nloc = 0;       // slice of the reads this GPU uploads and extracts keys for: [base, base + nloc)
+	char *arena[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // arena[shard_rank] is local
+	u32 *seg[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };    // bitmap range of GPU r (inside arena r)
+	bool seg_opened[8] = { false, false, false, false, false, false, false, false };             // mapped through CUDA IPC
+	size_t arena_bytes = 0, arena_bitmap_off = 0, arena_reads_off = 0, arena_bloom_off = 0;
+	size_t arena_rk_off[2] = { 0, 0 }, arena_ri_off[2] = { 0, 0 }; // received (key, id) pairs of the exchange
+	size_t arena_slots_off[2] = { 0, 0 }, arena_ids_off[2] = { 0, 0 };
 	bool dicts_sharded = false;
 	u32 shard_cap = 0;                    // nominal slots per dictionary shard (power of two)
 	u64 shard_nslots = 0;                 // slots reserved per shard: nominal + room for the spill at the end
-	size_t arena_slots_off[2] = { 0, 0 }; // byte offsets inside an arena
-	size_t arena_ids_off[2] = { 0, 0 };
-	bool seg_opened[8] = { false, false, false, false, false, false, false, false };
-	bool shard_ready = false;
+	u32 recv_cap = 0;                     // pairs a shard has room for
+	u32 bloom_seg_words = 0;              // words per Bloom segment (power of two); one segment per shard
+	int job_bloom = 1;                    // probe the Bloom filter before a remote table (HARCGPU_JOB_BLOOM=0 turns it off)
+	u32 job_epoch = 0;                    // barriers passed so far (the same on every rank)
+	bool shard_ready = false, job_reads_loaded = false;
 	int (*pool_exchange)(void *user, void *d_best, uint64_t count) = nullptr;
 	void *pool_exchange_user = nullptr;
+	int (*job_barrier_hook)(void *user) = nullptr; // ranks that share one GPU (tests): host barrier instead of the barrier kernel
+	void *job_barrier_user = nullptr;
 	// fused ingest (ingest.cu): reads with N as ASCII lines + their record numbers (input_N.dna, read_order_N.bin)
 	char *ing_N = nullptr;
 	u32 *ing_orderN = nullptr;
@@ -156,6 +168,21 @@ struct harcgpu_ctx {
 				return;
 			}
 	}
+	// tuning aid (HARCGPU_LAPS=1): device time between named points inside a phase, as "lap:<name>" of harcgpu_last_ms
+	int laps = -1;
+	cudaEvent_t evl0 = nullptr, evl1 = nullptr;
+	void lap(const char *name)
+	{
+		if (laps < 0) { const char *e = getenv("HARCGPU_LAPS"); laps = e && atoi(e) ? 1 : 0; }
+		if (!laps) return;
+		if (!evl0) { cudaEventCreate(&evl0); cudaEventCreate(&evl1); cudaEventRecord(evl0, st); }
+		cudaEventRecord(evl1, st);
+		cudaEventSynchronize(evl1);
+		float f = 0;
+		cudaEventElapsedTime(&f, evl0, evl1);
+		if (name) ms[std::string("lap:") + name] = f;
+		std::swap(evl0, evl1);
+	}
 	void tic() { cudaEventRecord(ev0, st); }
 	void toc(const char *phase)
 	{
@@ -175,11 +202,22 @@ int ing_ingest(harcgpu_ctx *c, const char *d_fastq, u64 nbytes, u64 *total_reads
 int ing_unpack_clean(harcgpu_ctx *c, char *d_out);
 // walk.cu
 int s1_init_claim(harcgpu_ctx *c, u32 *claim, u32 n);
+// job.cu
+void job_close(harcgpu_ctx *c);
+int job_barrier(harcgpu_ctx *c);
 // stage1.cu
 int s1_pack_reads(harcgpu_ctx *c, const void *d_ascii, u32 n);
+// pack n lines and store every packed read into `ndst` replicas (dst[r] points at the row of the first line)
+int s1_pack_reads_bcast(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *const *dst, int ndst);
+int s1_keys(harcgpu_ctx *c, const u64 *reads, u32 n, int words, int bitpos, int nbits, u32 id0, u64 *keys, u32 *ids);
 int s1_packN(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *out2, u64 *outN);
 struct DictShard { // where a dictionary shard of one job on several GPUs is built (inside the arena of ctx.h)
 	int rank, world;
+	// the (mixed key, id) pairs of the shard, already exchanged (ids ascending among equal keys); null: every key of
+	// `reads` is extracted here and the pairs of other shards are dropped (the reads are replicated anyway)
+	const u64 *pair_keys = nullptr;
+	const u32 *pair_ids = nullptr;
+	u32 npairs = 0;
 	ulonglong2 *slots;
 	u32 cap;   // nominal slots, power of two (fixes the home buckets)
 	u64 nslots; // slots the arena has room for: cap + spill

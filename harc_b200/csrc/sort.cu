@@ -200,18 +200,24 @@ __global__ void __launch_bounds__(256) runfix_kernel(u64 *__restrict__ keys, u32
 	const u64 k0 = keys[i];
 	if (i > 0 && (keys[i - 1] >> 32) == (k0 >> 32)) return; // not the head of a run
 	if (i + 1 >= n || (keys[i + 1] >> 32) != (k0 >> 32)) return; // run of one
+	// first a look at the run without buffering it: a run that is already in order (one dictionary bin of equal keys, however
+	// long -- repeats make such bins certain on real genomes) needs nothing; RUN_MAX only bounds the runs that have to be sorted
+	size_t len64 = 1;
+	bool sorted = true;
+	u64 prevk = k0;
+	while (i + len64 < n) {
+		const u64 kk = keys[i + len64];
+		if ((kk >> 32) != (k0 >> 32)) break;
+		if (kk < prevk) sorted = false;
+		prevk = kk;
+		len64++;
+	}
+	if (sorted) return;
+	if (len64 > RUN_MAX) { atomicMax(too_long, 1u); return; }
 	u64 k[RUN_MAX];
 	u32 v[RUN_MAX];
-	int len = 0;
-	bool sorted = true;
-	while (i + len < n && (keys[i + len] >> 32) == (k0 >> 32)) {
-		if (len == RUN_MAX) { atomicMax(too_long, 1u); return; }
-		k[len] = keys[i + len];
-		v[len] = vals[i + len];
-		if (len && k[len] < k[len - 1]) sorted = false;
-		len++;
-	}
-	if (sorted) return; // e.g. one bin of equal keys
+	const int len = (int)len64;
+	for (int a = 0; a < len; a++) { k[a] = keys[i + a]; v[a] = vals[i + a]; }
 	for (int a = 1; a < len; a++) { // stable insertion sort by the whole key
 		const u64 ka = k[a];
 		const u32 va = v[a];

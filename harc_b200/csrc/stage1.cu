@@ -33,8 +33,11 @@ __device__ __forceinline__ u32 codes4(u32 w)
 // four at a time from aligned 32-bit shared-memory words (funnel shift for the line's byte offset).
 // WITH_N (stage II pool, encoder.cpp:731-745): 'N' is stored as code 0 and flagged in a second word array at the
 // low bit of the base's pair; the reference's 3-bit code is then 2*code2 + nflag.
+// One job on several GPUs: the packed reads are stored into every GPU's replica by the kernel that produces them (plain
+// stores into NVLink peer memory; the pack and the all-gather of the packed reads are one kernel).
+struct PackDst { u64 *p[8]; int n; };
 template <bool WITH_N>
-__global__ void __launch_bounds__(256) pack_kernel(const char *__restrict__ ascii, u32 n, int L, int NWo, u64 *__restrict__ out,
+__global__ void __launch_bounds__(256) pack_kernel(const char *__restrict__ ascii, u32 n, int L, int NWo, PackDst dst,
                                                    u64 *__restrict__ outN)
 {
 	extern __shared__ uint4 stage4[];
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const char *__restrict__ asci
 			v |= (u64)squeeze4(c) << (8 * i);
 		}
 		const u64 m = lowmask(2 * nb);
-		out[(r0 + r) * NWo + k] = v & m;
+		for (int d = 0; d < dst.n; d++) dst.p[d][(r0 + r) * NWo + k] = v & m;
 		if (WITH_N) outN[(r0 + r) * NWo + k] = vn & m;
 	}
 }
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(256) unpack_kernel(const u64 *__restrict__ rea
 }
 
 // ------------------------------------------------------------------------------------------------ K2/K3 dictionary
-__global__ void __launch_bounds__(256) keys_kernel(const u64 *__restrict__ reads, u32 n, int words, int bitpos, int nbits,
+__global__ void __launch_bounds__(256) keys_kernel(const u64 *__restrict__ reads, u32 n, int words, int bitpos, int nbits, u32 id0,
                                                    u64 *__restrict__ keys, u32 *__restrict__ ids)
 {
 	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(256) keys_kernel(const u64 *__restrict__ reads
 	if (sh && q + 1 < words) v |= __ldg(&r[q + 1]) << (64 - sh);
 	if (nbits < 64) v &= (1ull << nbits) - 1;
 	keys[i] = key_mix(v); // the dictionary is built, stored and probed in mixed-key order (common.cuh)
-	ids[i] = i;
+	ids[i] = id0 + i;
 }
 
 // stage II keys (encoder.cpp:893-911): the reference's 3-bit code of base b is 2*code2 + nflag.  The window's 2-bit
@@ -268,7 +271,28 @@ int s1_pack_reads(harcgpu_ctx *c, const void *d_ascii, u32 n)
 	if (n == 0) return 0;
 	size_t smem = (size_t)PACK_RPB * (c->L + 1);
 	smem = (smem + 15) / 16 * 16 + 48; // slack: the last word of the last line reads up to 35 bytes past its start
-	pack_kernel<false><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, c->reads, nullptr);
+	PackDst dst;
+	dst.n = 1; dst.p[0] = c->reads;
+	pack_kernel<false><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, dst, nullptr);
+	CK(cudaGetLastError());
+	return 0;
+}
+int s1_pack_reads_bcast(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *const *out, int ndst)
+{
+	if (n == 0) return 0;
+	size_t smem = (size_t)PACK_RPB * (c->L + 1);
+	smem = (smem + 15) / 16 * 16 + 48;
+	PackDst dst;
+	dst.n = ndst;
+	for (int d = 0; d < 8; d++) dst.p[d] = d < ndst ? out[d] : nullptr;
+	pack_kernel<false><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, dst, nullptr);
+	CK(cudaGetLastError());
+	return 0;
+}
+int s1_keys(harcgpu_ctx *c, const u64 *reads, u32 n, int words, int bitpos, int nbits, u32 id0, u64 *keys, u32 *ids)
+{
+	if (n == 0) return 0;
+	keys_kernel<<<KL + cdiv(n, 256), 256, 0, c->st>>>(reads, n, words, bitpos, nbits, id0, keys, ids);
 	CK(cudaGetLastError());
 	return 0;
 }
@@ -278,8 +302,10 @@ int s1_packN(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *out2, u64 *outN)
 	if (n == 0) return 0;
 	size_t smem = (size_t)PACK_RPB * (c->L + 1);
 	smem = (smem + 15) / 16 * 16 + 48; // slack: the last word of the last line reads up to 35 bytes past its start
-	if (outN) pack_kernel<true><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, out2, outN);
-	else pack_kernel<false><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, out2, nullptr);
+	PackDst dst;
+	dst.n = 1; dst.p[0] = out2;
+	if (outN) pack_kernel<true><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, dst, outN);
+	else pack_kernel<false><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, dst, nullptr);
 	CK(cudaGetLastError());
 	return 0;
 }
@@ -328,6 +354,7 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 	}
 	const int bitpos = bits * ds, nbits = bits * (de - ds + 1);
 	d.bitpos = bitpos; d.nbits = nbits;
+	if (shard && shard->pair_keys) n = shard->npairs;
 	u64 *k_in = nullptr, *k_out = nullptr, *scan_tmp = nullptr;
 	u32 *id_in = nullptr, *head = nullptr, *binidx = nullptr, *d_total = nullptr;
 	u32 *id_alt = nullptr;
@@ -354,10 +381,14 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 	if (c->alloc(&k_in, n) || c->alloc(&k_out, n) || c->alloc(&id_in, n) || c->alloc(&head, n) || c->alloc(&binidx, n) ||
 	    c->alloc(&scan_tmp, scan_tmp_elems(n)) || c->alloc(&d_total, 1))
 		return -1;
-	if (bits == 2) keys_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(reads, n, words, bitpos, nbits, k_in, id_in);
+	if (shard && shard->pair_keys) {
+		// the pairs of this shard came through the key exchange (job.cu): sources in rank order = ids ascending among equal keys
+		CK(cudaMemcpyAsync(k_in, shard->pair_keys, 8 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+		CK(cudaMemcpyAsync(id_in, shard->pair_ids, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+	} else if (bits == 2) keys_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(reads, n, words, bitpos, nbits, 0u, k_in, id_in);
 	else keys3_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(reads, readsN, n, words, ds, de, k_in, id_in);
 	CK(cudaGetLastError());
-	if (shard) {
+	if (shard && !shard->pair_keys) {
 		// keep this GPU's keys, in id order (the scan keeps the order, so ids stay ascending inside a bin)
 		u32 *flag = head, *ex = binidx, kept = 0; // both arrays are free until the sort is done
 		u64 *k_f = k_out;

@@ -351,6 +351,7 @@ struct PoolArgs {
 	DictView d[2];
 	int L, thresh_s, maxsearch;
 	u64 *best;
+	u32 *flags;    // [0]: a scan of a bin beyond maxsearch ended with entries left; [1]: such a scan lowered a priority in this pass
 	u64 rank_bits; // rank << RANK_SHIFT
 	const u32 *bloom; u32 bloom_mask;
 	const u32 *T; // tile index
@@ -484,14 +485,35 @@ __global__ void __launch_bounds__(PP_THREADS) pool_probe_kernel(PoolArgs a)
 				for (int k = 0; k < NW; k++) rc[k] = tt[k] ^ lowmask(2 * L - 64 * k);
 				have_rc = true;
 			}
-			const u32 tlo = bsize > (u32)a.maxsearch ? bsize - (u32)a.maxsearch : 0u;
-			for (u32 e = bsize; e-- > tlo;) { // from the tail, no break: every read of the bin within thresh_s is taken (293-317)
-				const u32 rid = bin_entry(dv, bstart, bsize, e);
-				const u64 *p2 = a.pool + (size_t)rid * NW, *pn = a.poolN + (size_t)rid * NW;
-				int d = 0;
+			const u64 myprio = a.rank_bits | (g << 2) | (u64)q;
+			if (bsize <= (u32)a.maxsearch) {
+				for (u32 e = bsize; e-- > 0u;) { // from the tail, no break: every read of the bin within thresh_s is taken (293-317)
+					const u32 rid = bin_entry(dv, bstart, bsize, e);
+					const u64 *p2 = a.pool + (size_t)rid * NW, *pn = a.poolN + (size_t)rid * NW;
+					int d = 0;
 #pragma unroll
-				for (int k = 0; k < NW; k++) d += __popcll((rev ? rc[k] : w[k]) ^ __ldg(&p2[k])) + __popcll(__ldg(&pn[k]));
-				if (d <= a.thresh_s) atomicMin(&a.best[rid], a.rank_bits | (g << 2) | (u64)q);
+					for (int k = 0; k < NW; k++) d += __popcll((rev ? rc[k] : w[k]) ^ __ldg(&p2[k])) + __popcll(__ldg(&pn[k]));
+					if (d <= a.thresh_s) atomicMin(&a.best[rid], myprio);
+				}
+			} else {
+				// A bin beyond maxsearch.  The reference removes a read from its bins the moment a window takes it
+				// (encoder.cpp:1010-1031), so a later window scans the last maxsearch reads that are still LIVE (encoder.cpp:293).
+				// Here all windows probe at once: a read counts as live for this window unless a window of higher priority
+				// (= earlier in the reference's sequential order) holds it.  The host repeats the probe until no priority
+				// moves; priorities only fall and never below the sequential result, so the fixed point is that result.
+				int live = 0;
+				u32 e = bsize;
+				while (e-- > 0u && live < a.maxsearch) {
+					const u32 rid = bin_entry(dv, bstart, bsize, e);
+					if (*((volatile u64 *)&a.best[rid]) < myprio) continue; // taken earlier: not in the bin any more
+					live++;
+					const u64 *p2 = a.pool + (size_t)rid * NW, *pn = a.poolN + (size_t)rid * NW;
+					int d = 0;
+#pragma unroll
+					for (int k = 0; k < NW; k++) d += __popcll((rev ? rc[k] : w[k]) ^ __ldg(&p2[k])) + __popcll(__ldg(&pn[k]));
+					if (d <= a.thresh_s && atomicMin(&a.best[rid], myprio) > myprio) a.flags[1] = 1u;
+				}
+				if (live >= a.maxsearch && e != 0xffffffffu) a.flags[0] = 1u;
 			}
 		}
 	}
@@ -946,6 +968,7 @@ int s2_encode(harcgpu_ctx *c)
 	for (void *q : c->s2_keep) c->release(q);
 	c->s2_keep.clear();
 	c->tic();
+	c->lap(nullptr);
 
 	const u32 per = m ? 1 + (m - 1) / K : 1; // encoder.cpp:171
 	u32 *ns = nullptr, *ex = nullptr, *nat_idx = nullptr, *cs = nullptr, *cid = nullptr, *cstart = nullptr, *d_tot32 = nullptr;
@@ -976,6 +999,7 @@ int s2_encode(harcgpu_ctx *c)
 		CK(cudaStreamSynchronize(st));
 		TOT = tot + L;
 	}
+	c->lap("s2_layout");
 	const size_t cwords = (size_t)((TOT + 31) / 32);
 	if (c->alloc(&cons2, cwords + 2)) return -1;
 	CK(cudaMemsetAsync(cons2 + cwords, 0, 16, st));
@@ -1000,11 +1024,15 @@ int s2_encode(harcgpu_ctx *c)
 		}
 	}
 
+	c->lap("s2_consensus");
 	// ---- pool re-alignment
 	u64 *best = nullptr, *prio_u = nullptr, *iprio = nullptr;
 	u32 *af = nullptr, *exa = nullptr, *rid_u = nullptr, *irid = nullptr;
 	u32 M = 0, M_single = 0;
-	if (c->alloc(&best, P)) return -1;
+	u32 *pflags = nullptr;
+	PoolArgs pa;
+	bool have_probe = false;
+	if (c->alloc(&best, (size_t)P + 1) || c->alloc(&pflags, 2)) return -1;
 	if (P) {
 		fill64_kernel<<<KL + cdiv(P, 256), 256, 0, st>>>(best, P, NOBEST);
 		CK(cudaGetLastError());
@@ -1018,19 +1046,45 @@ int s2_encode(harcgpu_ctx *c)
 			a.d[l].dstart = c->d2[l].bitpos / 3; a.d[l].dend = a.d[l].dstart + c->d2[l].nbits / 3 - 1;
 			a.d[l].world = 0;
 		}
-		a.L = L; a.thresh_s = c->p.thresh_s; a.maxsearch = c->p.maxsearch; a.best = best;
+		a.L = L; a.thresh_s = c->p.thresh_s; a.maxsearch = c->p.maxsearch; a.best = best; a.flags = pflags;
 		a.rank_bits = (u64)(c->shard_world > 1 ? c->shard_rank : 0) << RANK_SHIFT;
 		a.bloom = c->bloom2; a.bloom_mask = c->bloom2_mask; a.T = tile_idx; a.nt = nt_host; a.cwords = cwords + 2;
-		u64 nwin = TOT - L + 1;
-		DISPATCH_NW(NWv, (pool_probe_kernel<NW><<<KL + cdiv(nwin, PP_COLS), PP_THREADS, 0, st>>>(a)));
-		CK(cudaGetLastError());
+		pa = a;
+		have_probe = true;
+	}
+	// One pass of the probe settles everything unless a bin beyond maxsearch was cut short; then the probe is repeated until
+	// no priority moves (see pool_probe_kernel).  One job on several GPUs: every GPU probed the same pool against its own
+	// contigs and the smallest priority over all GPUs wins -- all-reduce(min) after every pass, done by the caller's exchange
+	// hook (NCCL through torch.distributed in this repo); the word behind the priorities carries "somebody goes on".
+	for (int pass = 0; P && (have_probe || c->shard_world > 1); pass++) {
+		CK(cudaMemsetAsync(pflags, 0, 8, st));
+		if (have_probe) {
+			const u64 nwin = TOT - L + 1;
+			DISPATCH_NW(NWv, (pool_probe_kernel<NW><<<KL + cdiv(nwin, PP_COLS), PP_THREADS, 0, st>>>(pa)));
+			CK(cudaGetLastError());
+		}
+		u32 hf[2] = { 0, 0 };
+		CK(cudaMemcpyAsync(hf, pflags, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		// (the first pass also lowers priorities through the small bins, which the flag does not see: a cut-short scan always
+		// gets a second look)
+		bool again = hf[0] && (hf[1] || pass == 0);
+		if (c->shard_world > 1) {
+			if (!c->pool_exchange) { harcgpu_set_error("encode of one job on several GPUs needs harcgpu_set_pool_exchange"); return -1; }
+			const u64 word = again ? 0ull : NOBEST;
+			CK(cudaMemcpyAsync(best + P, &word, 8, cudaMemcpyHostToDevice, st));
+			CK(cudaStreamSynchronize(st));
+			if (c->pool_exchange(c->pool_exchange_user, best, (u64)P + 1)) { harcgpu_set_error("pool exchange hook failed"); return -1; }
+			u64 got = 0;
+			CK(cudaMemcpyAsync(&got, best + P, 8, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			again = got == 0ull;
+		}
+		c->ms["pool_passes"] = pass + 1;
+		if (!again) break;
+		if (pass >= 64) { harcgpu_set_error("pool re-alignment did not settle in 64 passes"); return -1; }
 	}
 	if (P && c->shard_world > 1) {
-		// one job on several GPUs: every GPU probed the same pool against its own contigs; the smallest priority over
-		// all GPUs wins (all-reduce(min) done by the caller's exchange hook, e.g. NCCL through torch.distributed)
-		if (!c->pool_exchange) { harcgpu_set_error("sharded encode needs harcgpu_set_pool_exchange"); return -1; }
-		CK(cudaStreamSynchronize(st));
-		if (c->pool_exchange(c->pool_exchange_user, best, P)) { harcgpu_set_error("pool exchange hook failed"); return -1; }
 		best_localize_kernel<<<KL + cdiv(P, 256), 256, 0, st>>>(best, P, c->shard_rank);
 		CK(cudaGetLastError());
 	}
@@ -1056,6 +1110,7 @@ int s2_encode(harcgpu_ctx *c)
 		CK(cudaStreamSynchronize(st));
 	}
 
+	c->lap("s2_pool");
 	// ---- merged list
 	const u64 F = (u64)m + M;
 	u32 *f_src = nullptr, *isN = nullptr, *exN = nullptr, *ordv = nullptr;
@@ -1094,6 +1149,7 @@ int s2_encode(harcgpu_ctx *c)
 	} else {
 		CK(cudaMemsetAsync(noff, 0, 8, st));
 	}
+	c->lap("s2_merge_emit");
 	// ---- unaligned pool reads
 	u32 *uf = nullptr, *exU = nullptr, *ulist = nullptr;
 	u32 U = 0, U_s = 0;
@@ -1134,6 +1190,7 @@ int s2_encode(harcgpu_ctx *c)
 		}
 	}
 
+	c->lap("s2_unaligned");
 	// ---- per file set views (encoder.cpp:169-196, 512-581)
 	c->sets.resize(K);
 	std::vector<u64> h_fs(K + 1), h_col(K + 1), h_no(K + 1);
@@ -1184,6 +1241,7 @@ int s2_encode(harcgpu_ctx *c)
 		memcpy(c->sets[k].rev_tail, &h_tail[16 * (size_t)k + 4], 8);
 	}
 	memcpy(c->single_tail, &h_tail[16 * (size_t)K], 4);
+	c->lap("s2_sets");
 	c->toc("encode");
 
 	c->esz.n_order = (u32)n_order; c->esz.n_order_N = (u32)n_order_N;
@@ -1194,7 +1252,7 @@ int s2_encode(harcgpu_ctx *c)
 		c->esz.aligned_N = M - M_single;
 	}
 	c->s2_keep.push_back(posb); c->s2_keep.push_back(noise); c->s2_keep.push_back(noisepos);
-	void *tmp[] = { tile_idx, ns, ex, nat_idx, cs, cid, cstart, inc, G, scan_tmp, d_tot32, d_tot64, cons2, best, prio_u, iprio, af, exa, rid_u, irid,
+	void *tmp[] = { pflags, tile_idx, ns, ex, nat_idx, cs, cid, cstart, inc, G, scan_tmp, d_tot32, d_tot64, cons2, best, prio_u, iprio, af, exa, rid_u, irid,
 	                f_src, f_kind, f_col, nm1, noff, revc, isN, exN, ordv, uf, exU, ulist, d_tail };
 	for (void *q : tmp) c->release(q);
 	c->encoded = true;

@@ -28,6 +28,8 @@ constexpr u32 FULL = 0xffffffffu;
 constexpr int DRY_HEADS = 4;          // left extension is skipped after this many heads in a row that stayed alone
 constexpr int STREAK_HEADS = 16;      // after this many, a head is searched over STREAK_SHIFTS shifts only
 constexpr int STREAK_SHIFTS = 8;
+constexpr u32 BIG_BIN = 64;           // bins of at least this many reads go through the cursor cache (advance())
+constexpr u32 TAILC_ENTRIES = 1u << 16;
 
 enum { S_SEARCH = 0, S_CHAINEND, S_RESTART, S_NEWHEAD, S_DONE };
 enum { P_DEAD = 0, P_PENDING, P_BIN, P_CAND };
@@ -49,6 +51,11 @@ struct WalkArgs {
 	// IPC, read and claimed over NVLink); this GPU's walkers start and restart only inside its own range
 	// [base, base + n_loc), whose words are `claim`.
 	u32 *claim;
+	// cursor cache of the big bins: entry = bin tag | index below which the bin still has unclaimed reads (see advance())
+	unsigned long long *tailc;
+	u32 tailc_mask;
+	const u32 *bloom;      // sharded dictionaries: this GPU's copy of the Bloom filter over all shards (null: no filter)
+	u32 bloom_seg_words;
 	u32 *hint; // sharded only: full-size local bitmap, bit cleared once this GPU knows the read is claimed (never authoritative)
 	u32 *seg[8];
 	u32 seg_per, base, n_loc;
@@ -381,10 +388,17 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 		p.home = true;
 		if (p.pend) {
 			probe_key(j, p.key, p.h);
+			c_probes++;
+			if (dv.world && a.bloom) {
+				// the table of this key lives on another GPU (world - 1 times out of world): ask the local filter first, most
+				// window keys are in no dictionary and then nothing crosses NVLink
+				u32 bw, bb;
+				job_bloom_pos(p.key, l, dv.world, a.bloom_seg_words, bw, bb);
+				if ((__ldg(&a.bloom[bw]) & bb) != bb) { p.pend = false; return; }
+			}
 			const ulonglong2 *sl = slots_of(p.key);
 			p.s0 = __ldg(&sl[p.h]);
 			p.s1 = __ldg(&sl[p.h + 1]);
-			c_probes++;
 		}
 	};
 
@@ -508,6 +522,41 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 			// next entry of this lane's bin that is unclaimed and within the Hamming threshold (scanned from the tail)
 			auto advance = [&](const u32 *hw, int hr, const u32 *hm) { // window word, bit offset and mask row of the lane's shift
 				ps = P_DEAD;
+				if (size >= BIG_BIN) {
+					// A bin of many reads (repeats: poly-A, tandem repeats, transposons).  The reference compacts a bin when a read
+					// is removed (reorder.cpp:409-432), so its scans only meet live ids; here claimed reads stay in the list and
+					// pile up at the tail, where every scan starts.  A small direct-mapped cache keeps, per big bin, an index above
+					// which every entry is known to be claimed (claims are never undone during a walk, so any stored value stays
+					// true; a lost or overwritten entry only costs time).  The claim bit is tested before the read is fetched.
+					const u32 shard = dv.world ? mix_shard(pc.key, dv.world) : 0u;
+					const u64 tag = ((u64)lo << 32) | ((u64)l << 31) | ((u64)shard << 28);
+					unsigned long long *ce = a.tailc + ((lo * 2u + (u32)l + shard * 0x9E3779B1u) & a.tailc_mask);
+					const bool cacheable = size < (1u << 28);
+					if (cacheable && left == size) { // first look at this bin in this round
+						const u64 e = *((volatile unsigned long long *)ce);
+						if ((e & ~0x0fffffffull) == tag) left = min(left, (u32)(e & 0x0fffffffull));
+					}
+					const u32 top = left;
+					bool tail_claimed = true; // every entry from `top` down to here was claimed
+					// many walkers: a probe gives up after 8 x maxsearch entries (one walker: the reference's scan, to the end)
+					u32 budget = a.extend != 0 ? 8u * (u32)a.maxsearch : 0xffffffffu;
+					while (left > 0 && seen < a.maxsearch && budget-- > 0u) {
+						left--;
+						const u32 rid = __ldg(&ids_of(pc.key)[lo + left]);
+						const u32 cw = ldvol(peek_word(a, rid));
+						if (!((cw >> (rid & 31)) & 1u)) continue; // removed from the bin in the reference (505-514)
+						if (tail_claimed) {
+							tail_claimed = false;
+							if (cacheable && left + 1 < top) *((volatile unsigned long long *)ce) = tag | (u64)(left + 1);
+						}
+						load_read<NW>(a.reads, rid, rw);
+						seen++;
+						c_cmp++;
+						if (hamming<NW>(hw, hr, hm, rw) <= a.thresh) { cand = rid; ps = P_CAND; break; }
+					}
+					if (tail_claimed && cacheable && left < top) *((volatile unsigned long long *)ce) = tag | (u64)left;
+					return;
+				}
 				while (left > 0 && seen < a.maxsearch) {
 					left--;
 					const u32 rid = size == 1 ? lo : __ldg(&ids_of(pc.key)[lo + left]);
@@ -534,25 +583,30 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 					pc.s1 = __ldg(&sl[pc.h + 1]);
 				}
 			};
+			// `win` = lane of the first candidate in sequential order once it is known (G before that)
+			int win = G;
 			while (true) {
-				if (ps == P_PENDING) resolve();
-				if (ps == P_BIN) advance(hw, hr, hm);
-				const u32 bc = __ballot_sync(gmask, ps == P_CAND) >> gbase, bp = __ballot_sync(gmask, ps == P_PENDING) >> gbase;
-				if (!(bc | bp)) break; // nothing matches in these shifts
-				if (!(bc && (!bp || (bc & (0u - bc)) < (bp & (0u - bp))))) continue;
-				const int win = __ffs(bc) - 1;
-				if (a.extend == 0) {
-					// the reference's walk (reorder.cpp:545-556): the first candidate in sequential order is claimed
-					int got = 0;
-					if (sub == win) {
-						got = try_claim(a, cand);
-						if (!got) { c_fail++; ps = P_BIN; }
+				const bool mine_to_work = sub > win || win == G; // with a winner known, only the lanes behind it go on (harvest)
+				if (mine_to_work && ps == P_PENDING) resolve();
+				if (mine_to_work && ps == P_BIN) advance(hw, hr, hm);
+				if (win == G) {
+					const u32 bc = __ballot_sync(gmask, ps == P_CAND) >> gbase, bp = __ballot_sync(gmask, ps == P_PENDING) >> gbase;
+					if (!(bc | bp)) break; // nothing matches in these shifts
+					if (!(bc && (!bp || (bc & (0u - bc)) < (bp & (0u - bp))))) continue;
+					win = __ffs(bc) - 1;
+					if (a.extend == 0) {
+						// the reference's walk (reorder.cpp:545-556): the first candidate in sequential order is claimed
+						int got = 0;
+						if (sub == win) {
+							got = try_claim(a, cand);
+							if (!got) { c_fail++; ps = P_BIN; }
+						}
+						got = __shfl_sync(gmask, got, gbase + win);
+						if (!got) { win = G; continue; }
+						found = true;
+						k_win = win;
+						break;
 					}
-					got = __shfl_sync(gmask, got, gbase + win);
-					if (!got) continue;
-					found = true;
-					k_win = win;
-					break;
 				}
 				// Harvest (not in the reference; with `extend`, i.e. never with one walker): the lanes behind the winner have
 				// already fetched their buckets of this round -- reads that start a few positions further on, which the next
@@ -565,10 +619,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 				// range lives on another GPU) are paid once for all of them.
 				// (Draining the multi-entry bins inside the harvest was tried: it finds more reads per round, 1.55 against
 				// 1.0 extra, but its one-lane dependent loads make the walk slower, 31.7 ms against 24.5.)
-				while (__any_sync(gmask, sub > win && (ps == P_PENDING || ps == P_BIN))) {
-					if (sub > win && ps == P_PENDING) resolve();
-					if (sub > win && ps == P_BIN) advance(hw, hr, hm);
-				}
+				if (__any_sync(gmask, sub > win && (ps == P_PENDING || ps == P_BIN))) continue;
 				const bool unsettled = sub >= win && ps == P_CAND && left > 0 && seen < a.maxsearch;
 				const u32 bu = __ballot_sync(gmask, unsettled) >> gbase;
 				// a lane whose bin has entries left ends the harvest behind its own shift: the lanes of the same shift (the
@@ -581,7 +632,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 				if (first_of_grp) { got = try_claim(a, cand); if (!got) c_fail++; }
 				bh = __ballot_sync(gmask, got != 0) >> gbase;
 				if (mine && !got) ps = P_BIN; // lost (or the same read as a lane in front): on with the bin if the round goes on
-				if (!bh) continue;            // every claim of the wave was lost to other walkers
+				if (!bh) { win = G; continue; } // every claim of the wave was lost to other walkers
 				found = true;
 				k_win = __ffs(bh) - 1;
 				bh &= bh - 1;
@@ -868,7 +919,7 @@ int s1_reorder(harcgpu_ctx *c)
 	// one job on several GPUs: this GPU's walkers own the id range [base, base + n_loc) for starts and restarts
 	const bool sharded = c->shard_world > 1;
 	if (sharded && (c->shard_n != n || !c->shard_ready)) {
-		harcgpu_set_error("sharded reorder: call harcgpu_shard_init/connect for these %u reads and harcgpu_shard_reset before every pass", n);
+		harcgpu_set_error("one job on several GPUs: call harcgpu_job_reorder (after harcgpu_job_init/connect/load_reads for these %u reads)", n);
 		return -1;
 	}
 	c->shard_ready = false; // a sharded pass consumes the reset
@@ -892,13 +943,15 @@ int s1_reorder(harcgpu_ctx *c)
 	if (extend && (c->alloc(&lrecs, (size_t)max_chunks * CHUNK) || c->alloc(&lprev, max_chunks))) return -1;
 	CK(cudaMemsetAsync(ctrs, 0, 8, st));
 	CK(cudaMemsetAsync(chunk_fill, 0, 4 * (size_t)max_chunks, st));
-	// one GPU: the bitmap.  Sharded: the authoritative ranges are armed by harcgpu_shard_reset before the barrier that
+	// one GPU: the bitmap.  Several GPUs: the authoritative ranges are armed by harcgpu_job_reorder before the barrier that
 	// precedes the walk; c->claim serves as this GPU's hint bitmap for the peers' ranges.
 	init_claim_kernel<<<KL + cdiv((n + 31) / 32, 256), 256, 0, st>>>(c->claim, n);
 	CK(cudaGetLastError());
 	u32 *stripe_done = nullptr;
-	if (c->alloc(&stripe_done, walkers)) return -1;
+	unsigned long long *tailc = nullptr;
+	if (c->alloc(&stripe_done, walkers) || c->alloc(&tailc, TAILC_ENTRIES)) return -1;
 	CK(cudaMemsetAsync(stripe_done, 0, 4 * (size_t)walkers, st));
+	CK(cudaMemsetAsync(tailc, 0xff, 8 * (size_t)TAILC_ENTRIES, st)); // no bin has this tag
 
 	a.reads = c->reads; a.n = n; a.L = c->L; a.maxmatch = c->p.maxmatch; a.thresh = c->p.thresh; a.maxsearch = c->p.maxsearch;
 	a.numdict = c->p.numdict; a.extend = extend;
@@ -908,18 +961,21 @@ int s1_reorder(harcgpu_ctx *c)
 		a.d[l].dstart = c->p.dict_start[ll]; a.d[l].dend = c->p.dict_end[ll];
 		a.d[l].world = c->dicts_sharded ? c->shard_world : 0;
 		for (int r = 0; r < 8; r++) {
-			const bool on = c->dicts_sharded && r < c->shard_world && c->seg[r];
-			a.d[l].sslots[r] = on ? (const ulonglong2 *)((const char *)c->seg[r] + c->arena_slots_off[ll]) : nullptr;
-			a.d[l].sids[r] = on ? (const u32 *)((const char *)c->seg[r] + c->arena_ids_off[ll]) : nullptr;
+			const bool on = c->dicts_sharded && r < c->shard_world && c->arena[r];
+			a.d[l].sslots[r] = on ? (const ulonglong2 *)(c->arena[r] + c->arena_slots_off[ll]) : nullptr;
+			a.d[l].sids[r] = on ? (const u32 *)(c->arena[r] + c->arena_ids_off[ll]) : nullptr;
 		}
 		a.kbits[l] = c->d1[ll].nbits;
 	}
+	a.bloom = c->dicts_sharded && c->job_bloom ? (const u32 *)(c->arena[c->shard_rank] + c->arena_bloom_off) : nullptr;
+	a.bloom_seg_words = c->bloom_seg_words;
 	a.claim = sharded ? c->seg[c->shard_rank] : c->claim; a.hint = c->claim; a.stripe_done = stripe_done; a.walkers = walkers;
 	for (int r = 0; r < 8; r++) a.seg[r] = sharded && r < c->shard_world ? c->seg[r] : nullptr;
 	a.seg_per = sharded ? c->seg_per : 0u; a.base = base; a.n_loc = n_loc; a.world = sharded ? c->shard_world : 1;
 	a.recs = recs; a.chunk_key = chunk_key; a.chunk_fill = chunk_fill; a.chunk_ctr = ctrs; a.max_chunks = max_chunks;
 	a.lrecs = lrecs; a.lprev = lprev; a.lchunk_ctr = ctrs + 1; a.max_lchunks = max_chunks;
 	a.counters = c->counters;
+	a.tailc = tailc; a.tailc_mask = TAILC_ENTRIES - 1;
 	// tuning aid: keep the claim bitmap (1 bit per read, hit by every candidate test and claim) in the persisting part of L2
 	bool l2win = false;
 	if (const char *e = getenv("HARCGPU_L2PERSIST")) {

@@ -38,8 +38,9 @@ typedef struct {
 	int extend;        /* left extension of new chains (not in the reference; same file format): 1 on, -1 off,
 	                      0 = on when more than one walker runs (one walker without it = the reference at num_thr=1) */
 	int lanes_per_walker; /* GPU lanes that cooperate on one walker: 16 or 32; 0 = default (32, one warp) */
-	int shard_dicts;   /* one job on several GPUs: 1 = both dictionaries sharded by key hash over the GPUs and probed
-	                      through NVLink peer memory (1/world of the tables per GPU), 0 = replicated on every GPU */
+	int shard_dicts;   /* one job on several GPUs: 1 = both dictionaries sharded by key hash over the GPUs (all-to-all of the
+	                      (key, id) pairs, probes through NVLink peer memory, 1/world of the tables per GPU), 0 = every
+	                      GPU builds and holds both dictionaries */
 } harcgpu_params;
 
 /* Sizes of everything stage II produced, so the caller can allocate before harcgpu_get_*.  (encoder.cpp:457-508) */
@@ -107,7 +108,7 @@ int harcgpu_load_pool_ingested(harcgpu_ctx *ctx);
 /* reorder.cpp:240-263 readDnaFile + 203-209 stringtobitset.  ascii = contents of input_clean.dna: n lines of
  * readlen chars in {A,C,G,T} + '\n' (host memory).  Copies to the device and packs 2 bits/base. */
 int harcgpu_load_reads(harcgpu_ctx *ctx, const char *ascii, uint32_t n);
-/* Same, from a buffer already resident in device memory (bench: the kernel-only figure). */
+/* Same, from a buffer already resident in device memory, 16-byte aligned (bench: the kernel-only figure). */
 int harcgpu_load_reads_device(harcgpu_ctx *ctx, const void *d_ascii, uint32_t n);
 /* reorder.cpp:277-394 constructdictionary (both dictionaries). */
 int harcgpu_build_dicts(harcgpu_ctx *ctx);
@@ -162,29 +163,53 @@ int harcgpu_get_globals(harcgpu_ctx *ctx, uint32_t *order, uint32_t *order_N, ui
  * per block of 32 entries), `tail` the read_order.bin.tail entries.  With NULL buffers only the sizes are written. */
 int harcgpu_get_packed_order(harcgpu_ctx *ctx, void *packed, uint32_t *tail, uint64_t *packed_bytes, uint32_t *tail_entries);
 
-/* ---- one job on several GPUs of one box (one process and one context per GPU) -------------------------------
- * Not in the reference (it is one process).  Every GPU holds all packed reads; the dictionaries are either replicated
- * or, with params.shard_dicts, sharded: GPU r builds and holds the key table and the id lists of the keys whose hash
- * falls into range r, and every walker probes the owner's table with plain loads over NVLink (the tables are read-only
- * during the walk).  What is always shared is the claimed-read bitmap (reorder.cpp:449 remainingreads + the lock arrays of reorder.cpp:436-442): it is cut into
- * `world` contiguous id ranges, range r lives on GPU r and the other GPUs read and claim it through NVLink peer memory
- * (CUDA IPC; bitmap range and dictionary shards of a GPU live in one allocation, so one handle per GPU is exchanged).
- * GPU r's walkers start and restart only inside range r but may claim any read, so the chains of all GPUs
- * partition the read set exactly as the threads of the reference do.  Stage II then runs per GPU on its own chains
- * (file set k = rank, encoder.cpp:169-196) against the same pool; which contig gets a pool read is settled by an
- * all-reduce(min) over the priority array, done by the caller's hook (NCCL through torch.distributed in this repo).
- * Call order per pass: load_reads (all reads, on every rank) -> shard_init -> [exchange the 64-byte handles] ->
- * shard_connect -> build_dicts -> shard_reset -> [barrier] -> reorder -> [barrier] -> get_reorder (own singletons) ->
- * [all-gather the singleton ids] -> load_pool_ids -> encode (calls the hook once) -> get_set(0) / get_globals. */
-int harcgpu_shard_init(harcgpu_ctx *ctx, int rank, int world, uint32_t n_total, void *ipc_handle_out /* 64 bytes */);
-int harcgpu_shard_connect(harcgpu_ctx *ctx, const void *handles /* world x 64 bytes, in rank order */);
-int harcgpu_shard_reset(harcgpu_ctx *ctx); /* re-arm this rank's range of the bitmap; barrier before the next reorder */
-/* Hook called once per harcgpu_encode of a sharded context with the device array of `count` int64 priorities: it must
+/* ---- one job on several GPUs of one box (one process and one context per GPU) ----------------------------------
+ * Not in the reference (it is one process); what is split is what its threads split: the key extraction of
+ * reorder.cpp:284-302, the walker starts of reorder.cpp:476-497 and the contig ranges of encoder.cpp:169-180.
+ *
+ * Every GPU owns one allocation, its arena, which the other GPUs map (CUDA IPC between processes).  GPU r uploads and
+ * packs its slice [base, base + n_local) of the clean reads; the pack kernel stores every packed read into the replica of
+ * every GPU over NVLink.  The two dictionaries are sharded by key (params.shard_dicts = 1): GPU r extracts the keys of its
+ * slice, the (key, id) pairs go to the owner of the key's hash range (an all-to-all done by plain stores into the owners'
+ * receive buffers), the owner sorts them and builds its shard of the key table; every GPU also holds a Bloom filter over
+ * all shards, so a walker asks a remote table only for keys that are almost certainly there.  With shard_dicts = 0 every
+ * GPU builds both dictionaries over all reads instead.  The claimed-read bitmap (reorder.cpp:449 remainingreads + the
+ * lock arrays of reorder.cpp:436-442) is cut into `world` contiguous id ranges, range r lives on GPU r and is read and
+ * claimed (atomicAnd) by the others through NVLink peer memory.  GPU r's walkers start and restart only inside range r
+ * but may claim any read, so the chains of all GPUs partition the read set exactly as the threads of the reference do.
+ * Stage II then runs per GPU on its own chains (file set k = rank, encoder.cpp:169-196) against the same pool; which
+ * contig gets a pool read is settled by an all-reduce(min) over the priority array, done by the caller's hook (NCCL
+ * through torch.distributed in this repo), as is the all-gather of the singleton ids.  The GPUs synchronise through
+ * barrier kernels inside these calls, so EVERY rank must make the same calls in the same order:
+ *   job_init -> [exchange the 64-byte handles] -> job_connect -> per pass: job_load_reads -> job_build_dicts ->
+ *   job_reorder -> [all-gather the singleton ids] -> load_pool_ids -> encode (calls the hook once) -> get_set(0) /
+ *   get_globals. */
+int harcgpu_job_init(harcgpu_ctx *ctx, int rank, int world, uint32_t n_total, uint32_t base, uint32_t n_local,
+                     void *ipc_handle_out /* 64 bytes, may be NULL */, void **local_ptr_out /* may be NULL */);
+/* handles: world x 64 bytes in rank order (other processes); or local_ptrs: the arenas of contexts of THIS process
+ * (what job_init gave as local_ptr_out), which lets one GPU stand in for several in tests. */
+int harcgpu_job_connect(harcgpu_ctx *ctx, const void *handles, void *const *local_ptrs);
+/* Only for ranks that are contexts of ONE process sharing one GPU (tests): the ranks then meet through this host hook
+ * (it must return 0 once every rank has called it) instead of the barrier kernel, because kernels of different streams
+ * of one GPU are not guaranteed to run side by side.  NULL restores the barrier kernel. */
+int harcgpu_job_set_barrier(harcgpu_ctx *ctx, int (*fn)(void *user), void *user);
+/* reorder.cpp:240-263 for this rank's slice (host / 16-byte aligned device buffer of n_local lines). */
+int harcgpu_job_load_reads(harcgpu_ctx *ctx, const char *ascii, uint32_t n_local);
+int harcgpu_job_load_reads_device(harcgpu_ctx *ctx, const void *d_ascii, uint32_t n_local);
+/* reorder.cpp:277-394 (harcgpu_build_dicts on a context of a job calls this). */
+int harcgpu_job_build_dicts(harcgpu_ctx *ctx);
+/* reorder.cpp:434-703 (harcgpu_reorder on a context of a job calls this). */
+int harcgpu_job_reorder(harcgpu_ctx *ctx);
+/* Hook called once per harcgpu_encode of a context of a job with the device array of `count` int64 priorities: it must
  * return 0 after replacing the array by its element-wise minimum over all ranks. */
 int harcgpu_set_pool_exchange(harcgpu_ctx *ctx, int (*fn)(void *user, void *d_best, uint64_t count), void *user);
 /* harcgpu_load_pool with the singletons given as ids into the reads of this context (the concatenation of all ranks'
- * read_order.bin.singleton); unaligned pool reads are written by rank 0 only. */
+ * read_order.bin.singleton; host or device memory); unaligned pool reads are written by rank 0 only. */
 int harcgpu_load_pool_ids(harcgpu_ctx *ctx, const uint32_t *singleton_ids, uint32_t n_s, const char *N_ascii, uint32_t n_N);
+/* Device pointer and element count of a result that the caller's plumbing moves between GPUs without a host copy:
+ * "singleton_ids" (read_order.bin.singleton of the last reorder), "order" (read_order.bin of the last reorder),
+ * "out_order" (read_order.bin of the last encode).  Valid until the next call that recomputes it. */
+int harcgpu_device_result(harcgpu_ctx *ctx, const char *name, const void **ptr, uint64_t *count);
 
 /* ---- the process contract, in-process --------------------------------------------------------------------- */
 /* `reorder.out <basedir>` (reorder.cpp:100-131) and `encoder.out <basedir>` (encoder.cpp:108-152): read and write

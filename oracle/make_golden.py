@@ -17,6 +17,7 @@ sys.path.insert(0, HERE)
 import refrun as R
 sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools"))
 import workload as W
+import numpy as np
 
 GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
 # name, reads, L, genome, rc, errors, seed
@@ -26,6 +27,9 @@ FIXTURES = [
     ("L250_err", 250, 250, 4000, False, True, 23),
     ("L63_RC_err", 700, 63, 3000, True, True, 24),
     ("L36_RC_err", 900, 36, 2500, True, True, 25),
+    # repeat-rich (refrun.repeat_rich_genome, scaled down): a poly-A run, a tandem repeat and duplications give dictionary
+    # bins beyond maxsearch = 1000 in stage I and bins of hundreds in the stage II pool
+    ("L36_repeats", 9000, 36, "repeats", True, True, 26),
 ]
 S1 = ["temp.dna", "temp.dna.singleton", "read_rev.txt", "tempflag.txt", "temppos.txt", "read_order.bin", "read_order.bin.singleton"]
 
@@ -38,7 +42,13 @@ def main():
         with tempfile.TemporaryDirectory() as tmp:
             # inputs from tools/simreads.c (the reference's gen_fastq overruns its buffer on genomes this small);
             # laid out as preprocess.cpp:98-131 writes them.  Everything under s1/ s2/ comes from the reference binaries.
-            W.write_dir(W.make(n, L, G, rc=rc, errors=err, seed=seed), tmp)
+            if G == "repeats":
+                g = R.repeat_rich_genome(seed, unique=3000, polyA=3000, tandem_unit=5, tandem_copies=100, dup_len=60, dup_copies=6,
+                                         div_len=80, div_copies=2)
+                W.write_dir(W.make(n, L, len(g), rc=rc, errors=err, seed=seed, genome=g), tmp)
+                G = len(g)
+            else:
+                W.write_dir(W.make(n, L, G, rc=rc, errors=err, seed=seed), tmp)
             out = os.path.join(tmp, "output")
             shutil.copytree(out, os.path.join(dst, "in"))
             R.dictdump(tmp, L, os.path.join(dst, "dict1.bin"))

@@ -41,10 +41,38 @@ def _run(cmd, cwd, timeout=3600, quiet=True):
     return dt, r.stdout.decode(errors="replace")
 
 
-def make_genome(path, nbases, seed=1, line=100):
-    """Seeded uniform i.i.d. ACGT FASTA (the reference has no genome generator)."""
+def repeat_rich_genome(seed=1, unique=300000, polyA=80000, tandem_unit=7, tandem_copies=2000, dup_len=300, dup_copies=60,
+                       div_len=1000, div_copies=20):
+    """A genome with what real ones have and i.i.d. ones lack: a long poly-A run, a tandem repeat of a short unit, an exact
+    dispersed duplication and a family of 1 %-diverged copies, between stretches of unique sequence.  Dictionary bins of
+    thousands of reads (beyond maxsearch = 1000) in both stages follow from it."""
     rng = np.random.default_rng(seed)
-    g = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=nbases, dtype=np.uint8)]
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    rnd = lambda n: acgt[rng.integers(0, 4, size=n, dtype=np.uint8)]
+    parts = [rnd(unique // 4), np.full(polyA, ord("A"), np.uint8), rnd(unique // 4), np.tile(rnd(tandem_unit), tandem_copies)]
+    dup = rnd(dup_len)
+    fam = rnd(div_len)
+    gap = unique // 2 // (dup_copies + div_copies + 1)
+    for k in range(dup_copies + div_copies):
+        parts.append(rnd(gap))
+        if k % 4 == 3 and k // 4 < div_copies:
+            c = fam.copy()
+            pos = rng.integers(0, div_len, size=div_len // 100)
+            c[pos] = acgt[rng.integers(0, 4, size=pos.size, dtype=np.uint8)]
+            parts.append(c)
+        else:
+            parts.append(dup)
+    parts.append(rnd(gap))
+    return np.concatenate(parts)
+
+
+def make_genome(path, nbases, seed=1, line=100, bases=None):
+    """Seeded uniform i.i.d. ACGT FASTA (the reference has no genome generator); `bases` writes a given genome."""
+    rng = np.random.default_rng(seed)
+    if bases is not None:
+        g, nbases = bases, len(bases)
+    else:
+        g = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=nbases, dtype=np.uint8)]
     nl = (nbases + line - 1) // line
     with open(path, "wb") as f:
         f.write(b">synthetic seed=%d len=%d\n" % (seed, nbases))
@@ -139,22 +167,26 @@ def standin_size(basedir, include_order=False):
     """Stage III stand-in (bsc/7z are absent): bz2 -9 for the bsc streams, xz for the 7z ones.
     Returns (total_bytes, per-stream dict).  Same function is applied to the reference's and to our output."""
     out = os.path.join(basedir, "output")
-    sizes = {}
+    jobs = {}  # name -> (function, bytes); the compressors release the GIL, so the streams are squeezed side by side
     for stem in BSC_STEMS:
-        sizes[stem] = len(bz2.compress(_cat(out, stem), 9))
+        jobs[stem] = (lambda b: len(bz2.compress(b, 9)), _cat(out, stem))
     for stem in LZMA_STEMS:
-        sizes[stem] = len(lzma.compress(_cat(out, stem), preset=6))
+        jobs[stem] = (lambda b: len(lzma.compress(b, preset=6)), _cat(out, stem))
+    extra = {}
     for f in ("read_singleton.txt", "input_N.dna"):
-        sizes[f] = len(bz2.compress(open(os.path.join(out, f), "rb").read(), 9))
+        jobs[f] = (lambda b: len(bz2.compress(b, 9)), open(os.path.join(out, f), "rb").read())
         t = os.path.join(out, f + ".tail")
-        if os.path.exists(t):
-            sizes[f] += os.path.getsize(t)
-    sizes["read_meta.txt"] = len(lzma.compress(open(os.path.join(out, "read_meta.txt"), "rb").read()))
+        extra[f] = os.path.getsize(t) if os.path.exists(t) else 0
+    jobs["read_meta.txt"] = (lambda b: len(lzma.compress(b)), open(os.path.join(out, "read_meta.txt"), "rb").read())
     if include_order:
         for f in ("read_order.bin", "read_order_N.bin", "read_order_N_pe.bin"):
             p = os.path.join(out, f)
             if os.path.exists(p):
-                sizes[f] = len(lzma.compress(open(p, "rb").read(), preset=6))
+                jobs[f] = (lambda b: len(lzma.compress(b, preset=6)), open(p, "rb").read())
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        futs = {k: ex.submit(fn, data) for k, (fn, data) in jobs.items()}
+        sizes = {k: f.result() + extra.get(k, 0) for k, f in futs.items()}
     return sum(sizes.values()), sizes
 
 

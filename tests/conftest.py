@@ -4,6 +4,10 @@ import sys
 
 import pytest
 
+# several contexts of one process stand in for several GPUs in tests/test_multigpu_gpu.py: their barrier kernels spin on one
+# another, so every stream needs a hardware queue of its own (must be set before CUDA starts)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))

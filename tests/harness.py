@@ -63,6 +63,26 @@ def make_dataset(root, name, n, L, genome, rc=False, errors=False, seed=1):
     return d
 
 
+def make_repeat_dataset(root, name, n, L, rc=True, errors=True, seed=1):
+    """Like make_dataset on refrun.repeat_rich_genome: poly-A, tandem repeats, duplications -> bins beyond maxsearch."""
+    d = os.path.join(root, name)
+    if os.path.exists(os.path.join(d, "output", "numreads.bin")):
+        return d
+    os.makedirs(d, exist_ok=True)
+    R.make_genome(os.path.join(d, "g.fa"), 0, seed=seed, bases=R.repeat_rich_genome(seed))
+    R.gen_fastq(os.path.join(d, "g.fa"), os.path.join(d, "r.fastq"), n, L, rc=rc, errors=errors)
+    R.preprocess(os.path.join(d, "r.fastq"), d, L)
+    return d
+
+
+def dataset(root, case, seed):
+    """case = (name, reads, L, genome, rc, errors); genome == 'repeats' -> the repeat-rich genome."""
+    name, n, L, G, rc, err = case
+    if G == "repeats":
+        return make_repeat_dataset(root, name, n, L, rc, err, seed)
+    return make_dataset(root, name, n, L, G, rc, err, seed)
+
+
 def clone(src, dst, names=None):
     shutil.rmtree(dst, ignore_errors=True)
     return R.copy_stage(src, dst, names)

@@ -16,13 +16,14 @@ CASES = [
     ("o250", 4000, 250, 100000, False, True),
     ("o63", 12000, 63, 80000, True, True),
     ("o36", 12000, 36, 60000, True, True),
+    ("orep100", 150000, 100, "repeats", True, True),   # poly-A / tandem repeats / duplications: bins beyond maxsearch in both stages
 ]
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_both_stages_byte_identical_at_one_thread(workroot, case):
     name, n, L, G, rc, err = case
-    d = H.make_dataset(workroot, name, n, L, G, rc, err, seed=31)
+    d = H.dataset(workroot, case, seed=31)
     r = H.clone(d, d + ".ref")
     R.reorder(r, L, 1)
     o = H.clone(d, d + ".ora")

@@ -59,3 +59,24 @@ def test_top_half_route_orders_runs_that_share_their_top_half():
     rng.shuffle(keys)
     _check(ctx, keys, 1)
     ctx.close()
+
+
+def test_long_bins_of_equal_keys_stay_on_the_fast_path():
+    """A dictionary bin of more than 32 reads (equal keys: certain on repetitive genomes) is already in order after the four
+    passes over the top half: the fix-up must leave it alone instead of falling back to the full sort."""
+    import harc_b200
+    ctx = harc_b200.HarcGpu(100)
+    rng = np.random.default_rng(12)
+    base = rng.integers(0, 2 ** 64, size=100000, dtype=np.uint64)
+    bins = [np.full(n, k, dtype=np.uint64) for n, k in ((33, 0xAAAA000011112222), (1000, 0x0123456789ABCDEF), (50000, 0))]
+    # and a run of two different keys with one top half, of which one is a long bin
+    mixed = np.concatenate([np.full(400, 0xBEEF000000000007, dtype=np.uint64), np.full(3, 0xBEEF000000000003, dtype=np.uint64)])
+    keys = np.concatenate([base] + bins + [mixed])
+    rng.shuffle(keys)
+    l0 = harc_b200.launch_count()
+    _check(ctx, keys, 1)
+    fast = harc_b200.launch_count() - l0
+    l0 = harc_b200.launch_count()
+    _check(ctx, keys[: len(base)], 1)
+    assert fast - (harc_b200.launch_count() - l0) < 8, "long bins of equal keys must not trigger the eight-pass fallback"
+    ctx.close()

@@ -16,6 +16,7 @@ CASES = [
     ("s250", 8000, 250, 150000, False, True),
     ("s63", 20000, 63, 100000, True, True),
     ("s36", 20000, 36, 60000, True, True),
+    ("rep100", 150000, 100, "repeats", True, True),   # poly-A, tandem repeats, duplications: bins beyond maxsearch in both stages
 ]
 
 
@@ -30,7 +31,7 @@ def test_dictionary_bit_exact(gpu, workroot, case):
     """Dictionary contents (keys, bin sizes, ids inside bins) == the reference's own constructdictionary (dictdump
     wrapper around the unmodified reorder.cpp)."""
     name, n, L, G, rc, err = case
-    d = H.make_dataset(workroot, name, n, L, G, rc, err, seed=11)
+    d = H.dataset(workroot, case, seed=11)
     dump = os.path.join(d, "dict1.bin")
     R.dictdump(d, L, dump)
     raw = np.fromfile(dump, dtype=np.uint8)
@@ -59,7 +60,7 @@ def test_dictionary_bit_exact(gpu, workroot, case):
 def test_reorder_one_walker_bit_exact(gpu, workroot, case):
     """With one walker the GPU chain walk must reproduce the reference at num_thr=1 byte for byte (all seven files)."""
     name, n, L, G, rc, err = case
-    d = H.make_dataset(workroot, name, n, L, G, rc, err, seed=11)
+    d = H.dataset(workroot, case, seed=11)
     o = H.clone(d, d + ".oracle")
     H.oracle_reorder(o, L, 1)
     g = H.clone(d, d + ".gpu")

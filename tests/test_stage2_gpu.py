@@ -17,6 +17,7 @@ CASES = [
     ("s250", 8000, 250, 150000, False, True),
     ("s63", 20000, 63, 100000, True, True),
     ("s36", 20000, 36, 60000, True, True),
+    ("rep100", 150000, 100, "repeats", True, True),   # poly-A, tandem repeats, duplications: bins beyond maxsearch in both stages
 ]
 STAGE2_GLOBAL = ["read_meta.txt", "read_order.bin", "read_order_N_pe.bin", "read_singleton.txt", "read_singleton.txt.tail", "input_N.dna"]
 
@@ -38,7 +39,7 @@ def gpu():
 
 def _stage1(workroot, case):
     name, n, L, G, rc, err = case
-    d = H.make_dataset(workroot, name, n, L, G, rc, err, seed=11)
+    d = H.dataset(workroot, case, seed=11)
     s1 = d + ".s1"
     if not os.path.exists(os.path.join(s1, "output", "temp.dna")):
         H.clone(d, s1)
@@ -112,7 +113,7 @@ def test_pipeline_lossless_through_reference_decoder(gpu, workroot, case):
     """GPU reorder (many walkers) + GPU encode, decoded by the reference's unmodified decoder.out: the multiset of
     reads must equal the input (harc -d order-free contract)."""
     name, n, L, G, rc, err = case
-    d = H.make_dataset(workroot, name, n, L, G, rc, err, seed=11)
+    d = H.dataset(workroot, case, seed=11)
     g = H.clone(d, d + ".pipe")
     ctx = gpu.HarcGpu(L, walkers=32, file_sets=3)
     ctx.reorder_dir(g)
@@ -130,7 +131,7 @@ def test_pipeline_lossless_through_reference_decoder(gpu, workroot, case):
 def test_in_memory_handoff_equals_file_path(gpu, workroot):
     """reorder -> encode on one context (streams stay on the device) == reorder_dir -> encode_dir through files."""
     name, n, L, G, rc, err = CASES[0]
-    d = H.make_dataset(workroot, name, n, L, G, rc, err, seed=11)
+    d = H.dataset(workroot, case, seed=11)
     g = H.clone(d, d + ".mem")
     out = os.path.join(g, "output")
     ctx = gpu.HarcGpu(L, walkers=1, file_sets=2)
