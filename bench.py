@@ -356,9 +356,9 @@ def run_single(args, rank, world, local, dist, json_fd):
             def lap(name):
                 t.append(time.perf_counter())
                 self.ms[name] = self.ms.get(name, 0.0) + 1000.0 * (t[-1] - t[-2])
+            c.stage_nreads(hN_np)  # the reads with N go first, on the copy stream: their upload overlaps stage I
             c.load_reads(hC_np, n_clean)
             lap("load_reads(H2D+pack)")
-            c.stage_nreads(hN_np)  # upload of the reads with N overlaps stage I
             c.reorder()
             lap("reorder")
             c.load_pool(None, None, hN_np)
@@ -420,7 +420,7 @@ def run_single(args, rank, world, local, dist, json_fd):
     # ---- e2e: one job at a time, then two jobs in flight (two contexts, one host thread each)
     ms_e2e = ms_pipe = float("nan")
     job = None
-    pipe_note = None
+    pipe_note = pipe_host = None
     if not args.no_e2e:
         job = HostJob(ctx)
         job.step()  # warm the host path
@@ -434,6 +434,8 @@ def run_single(args, rank, world, local, dist, json_fd):
             for j in jobs[1:]:
                 j.step()
                 j.step()
+            for j in jobs:
+                j.ms.clear()
             per = max(2, args.steps)
 
             def worker(j):
@@ -454,6 +456,7 @@ def run_single(args, rank, world, local, dist, json_fd):
             torch.cuda.synchronize()
             ms_pipe = max(e0.elapsed_time(e) for e in ends) / (per * len(jobs))
             pipe_note = "%d jobs in flight (one context and one host thread each), %d jobs in all" % (len(jobs), per * len(jobs))
+            pipe_host = [{k: v / per for k, v in j.ms.items()} for j in jobs]
             for j in jobs[1:]:
                 j.c.close()
 
@@ -487,6 +490,7 @@ def run_single(args, rank, world, local, dist, json_fd):
                       "ms_per_step": ms_pipe if e2e_pipe else ms_e2e,
                       "what": ("pipelined: " + pipe_note) if e2e_pipe else "one job at a time",
                       "single_job": {"value": e2e_single, "ms_per_step": ms_e2e, "host_wall_ms": host_ms},
+                      "pipelined_host_wall_ms_per_job": pipe_host,
                       "h2d_bytes_per_step": int(h_clean.numel() + h_N.numel()), "d2h_bytes_per_step": int(job.d2h),
                       "pcie_note": "H2D of %.2f GB per job: at the ~55 GB/s a Gen5 x16 link delivers that alone is %.0f ms, the floor of a step"
                                    % ((h_clean.numel() + h_N.numel()) / 1e9, (h_clean.numel() + h_N.numel()) / 55e9 * 1e3)}
@@ -573,39 +577,43 @@ def run_one_job(args, rank, world, local, dist, json_fd):
         dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, sampler=None):
+    detail = {}
+
+    def timed(fn, steps, sampler=None, tag=None):
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ph = {p: 0.0 for p in phases}
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        phl = {p: [] for p in phases}
         if sampler:
             sampler.start()
         l0 = harc_b200.launch_count()
-        e0.record(stream)
-        for _ in range(steps):
+        m0 = ctx.last_ms("cudaMalloc_calls")
+        ev[0].record(stream)
+        for k in range(steps):
             fn()
+            ev[k + 1].record(stream)
             for p in phases:
-                ph[p] += max(0.0, ctx.last_ms(p))
-        e1.record(stream)
+                phl[p].append(max(0.0, ctx.last_ms(p)))
         barrier()
         if sampler:
             sampler.stop.set()
-        ms = e0.elapsed_time(e1) / steps
-        t = torch.tensor([ms] + [ph[p] / steps for p in phases], device="cuda", dtype=torch.float64)
+        ms = ev[0].elapsed_time(ev[-1]) / steps
+        per_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+        t = torch.tensor([ms] + [sum(phl[p]) / steps for p in phases], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)  # the slowest rank, phase by phase
         t = t.tolist()
+        if tag:
+            detail[tag] = {"per_step_ms_rank0": per_step, "phases_ms_per_step_rank0": phl,
+                           "cudaMalloc_calls_in_timed_region_rank0": int(ctx.last_ms("cudaMalloc_calls") - m0)}
         return t[0], dict(zip(phases, t[1:])), (harc_b200.launch_count() - l0) // steps
 
     for _ in range(args.warmup):
         step_device()
     sampler = ClockSampler(local)
-    ms_dev, ph, launches = timed(step_device, args.steps, sampler)
-    cnt = ctx.counters()
-    m, s, u = ctx.reorder_counts()
-    es = last["res"]["sizes"]
+    ms_dev, ph, launches = timed(step_device, args.steps, sampler, "device")
     ms_e2e = float("nan")
     if not args.no_e2e:
         step_host()
-        ms_e2e, _, _ = timed(step_host, args.steps)
+        ms_e2e, _, _ = timed(step_host, args.steps, None, "e2e")
     else:
         step_host()
     cnt = ctx.counters()       # the verify block and the counters are those of the LAST pass (the walk is not deterministic)
@@ -660,8 +668,8 @@ def run_one_job(args, rank, world, local, dist, json_fd):
                 dN = torch.empty(wf["withN"].size + 16, dtype=torch.uint8, device="cuda")
                 dN[: wf["withN"].size].copy_(torch.from_numpy(wf["withN"]))
                 st1 = torch.cuda.ExternalStream(c1.stream())
-                ms1 = []
-                for it in range(3):
+                ms1, ph1 = [], []
+                for it in range(6):
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     torch.cuda.synchronize()
                     e0.record(st1)
@@ -673,10 +681,12 @@ def run_one_job(args, rank, world, local, dist, json_fd):
                     e1.record(st1)
                     torch.cuda.synchronize()
                     ms1.append(e0.elapsed_time(e1))
+                    ph1.append({p: c1.last_ms(p) for p in phases})
                 m1, s1, u1 = c1.reorder_counts()
-                one_gpu = {"ms_per_step": min(ms1[1:]), "Mreads_per_s": cfg["reads"] / min(ms1[1:]) / 1e3,
-                           "phases_ms": {p: c1.last_ms(p) for p in phases}, "chain_heads": u1, "singletons": s1,
-                           "what": "the whole workload on rank 0's GPU alone (plain single-GPU path), best of 2 after 1 warm-up, device-timed, "
+                best = int(np.argmin(ms1[3:])) + 3
+                one_gpu = {"ms_per_step": ms1[best], "Mreads_per_s": cfg["reads"] / ms1[best] / 1e3, "all_steps_ms": ms1,
+                           "phases_ms": ph1[best], "chain_heads": u1, "singletons": s1,
+                           "what": "the whole workload on rank 0's GPU alone (plain single-GPU path), best of 3 after 3 warm-ups, device-timed, "
                                    "measured in this run while the other ranks wait"}
                 c1.close()
                 del dC, dN, wf
@@ -715,7 +725,7 @@ def run_one_job(args, rank, world, local, dist, json_fd):
                                        "walk_kernel<%d, %d>, per GPU" % (ctx.NW(), args.lanes or 32)),
             "e2e": {"value": e2e, "unit": "Mreads/s", "ms_per_step": ms_e2e, "what": "one job at a time; every rank uploads its slice from pinned host "
                     "memory and reads back its file set", "h2d_bytes_per_step": int(h_clean.numel() + h_N.numel()) * world, "d2h_bytes_per_step": int(last.get("d2h", 0)) * world},
-            "exchange_bytes_per_step": comm_bytes, "verify": verify, "one_gpu_same_workload": one_gpu, "laps_ms_rank0": laps or None,
+            "exchange_bytes_per_step": comm_bytes, "verify": verify, "one_gpu_same_workload": one_gpu, "laps_ms_rank0": laps or None, "detail": detail,
             "gpu_launches": int(launches), "allocator": {"device_peak_MB": ctx.last_ms("peak_MB"), "cudaMalloc_calls": ctx.last_ms("cudaMalloc_calls")},
             "clocks": sampler.summary(), "commit": git_head(),
         }

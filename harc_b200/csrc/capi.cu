@@ -92,6 +92,7 @@ void harcgpu_destroy(harcgpu_ctx *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->st);
 	job_close(c);
+	if (c->st_bcast) { cudaStreamSynchronize(c->st_bcast); cudaStreamDestroy(c->st_bcast); cudaEventDestroy(c->ev_packed); cudaEventDestroy(c->ev_bcast); }
 	if (c->st_copy) { cudaStreamSynchronize(c->st_copy); cudaStreamDestroy(c->st_copy); cudaEventDestroy(c->ev_staged); cudaEventDestroy(c->ev_order); }
 	for (auto &b : c->live) cudaFree(b.p);
 	c->trim();
@@ -141,18 +142,42 @@ int harcgpu_load_reads_device(harcgpu_ctx *c, const void *d_ascii, u32 n)
 	return 0;
 }
 
+static int ensure_copy_stream(harcgpu_ctx *c)
+{
+	if (!c->st_copy) {
+		CK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
+	}
+	return 0;
+}
+
+// The upload is cut into chunks on the copy stream and every chunk is packed as soon as it has arrived, so the pack runs
+// under the copy (and the copies of several contexts that share the link interleave chunk by chunk).
 int harcgpu_load_reads(harcgpu_ctx *c, const char *ascii, u32 n)
 {
 	if (!c || (!ascii && n)) { harcgpu_set_error("null argument"); return -1; }
 	CK(cudaSetDevice(c->device));
+	if (ensure_copy_stream(c)) return -1;
 	char *d = nullptr;
-	size_t bytes = (size_t)n * (c->L + 1);
+	const size_t line = (size_t)c->L + 1, bytes = (size_t)n * line;
 	if (c->alloc(&d, bytes + 16)) return -1;
-	CK(cudaMemcpyAsync(d, ascii, bytes, cudaMemcpyHostToDevice, c->st));
-	int rc = harcgpu_load_reads_device(c, d, n);
-	CK(cudaStreamSynchronize(c->st));
+	if (reset_stage1(c, n)) return -1;
+	// the staging block may still be in use by work queued on the compute stream: order the copies behind it
+	CK(cudaEventRecord(c->ev_order, c->st));
+	CK(cudaStreamWaitEvent(c->st_copy, c->ev_order, 0));
+	c->tic();
+	const u32 chunk = 1u << 18; // reads per chunk: a multiple of 64, so every chunk starts on a 16-byte boundary
+	for (u32 r0 = 0; r0 < n; r0 += chunk) {
+		const u32 nr = std::min<u32>(chunk, n - r0);
+		CK(cudaMemcpyAsync(d + (size_t)r0 * line, ascii + (size_t)r0 * line, (size_t)nr * line, cudaMemcpyHostToDevice, c->st_copy));
+		CK(cudaEventRecord(c->ev_order, c->st_copy));
+		CK(cudaStreamWaitEvent(c->st, c->ev_order, 0));
+		if (s1_pack_reads_to(c, d + (size_t)r0 * line, nr, c->reads + (size_t)r0 * c->NW)) return -1;
+	}
+	c->toc("pack");
 	c->release(d);
-	return rc;
+	return 0;
 }
 
 // ---- fused ingest: preprocess.cpp:49-138 + reorder.cpp:240-263 ------------------------------------------------
@@ -396,11 +421,7 @@ int harcgpu_stage_nreads(harcgpu_ctx *c, const char *N_ascii, uint32_t n_N)
 {
 	if (!c || (n_N && !N_ascii)) { harcgpu_set_error("null argument"); return -1; }
 	CK(cudaSetDevice(c->device));
-	if (!c->st_copy) {
-		CK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
-		CK(cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming));
-		CK(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
-	}
+	if (ensure_copy_stream(c)) return -1;
 	c->release(c->staged_N);
 	c->staged_N = nullptr; c->staged_host = nullptr; c->staged_n = 0;
 	if (!n_N) return 0;

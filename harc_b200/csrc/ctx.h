@@ -57,6 +57,9 @@ struct harcgpu_ctx {
 	int job_bloom = 1;                    // probe the Bloom filter before a remote table (HARCGPU_JOB_BLOOM=0 turns it off)
 	u32 job_epoch = 0;                    // barriers passed so far (the same on every rank)
 	bool shard_ready = false, job_reads_loaded = false;
+	cudaStream_t st_bcast = nullptr;      // side stream of the broadcast of this GPU's packed slice
+	cudaEvent_t ev_packed = nullptr, ev_bcast = nullptr;
+	bool bcast_pending = false;
 	int (*pool_exchange)(void *user, void *d_best, uint64_t count) = nullptr;
 	void *pool_exchange_user = nullptr;
 	int (*job_barrier_hook)(void *user) = nullptr; // ranks that share one GPU (tests): host barrier instead of the barrier kernel
@@ -102,15 +105,27 @@ struct harcgpu_ctx {
 
 	// Device memory: a caching allocator private to the context.  Every kernel and copy of a context runs on its one
 	// stream, so a block can be handed out again as soon as it is released (reuse is stream-ordered by construction).
-	// A request takes the smallest cached block that is large enough but at most 25 % (+2 MiB) larger; otherwise it
-	// goes to cudaMalloc.  A pass repeats the sizes of the pass before it, so after the first pass no allocation
+	// A request takes the smallest cached block that is large enough but at most 30 % larger; otherwise it goes to
+	// cudaMalloc.  A pass repeats the sizes of the pass before it, so after the first pass no allocation
 	// reaches the driver.  (cudaMallocAsync was measured here to spend hundreds of ms per pass remapping its pool when
 	// block sizes vary between calls.)
 	struct Block { void *p; size_t bytes; };
 	std::vector<Block> live, cached;
 	size_t cached_bytes = 0, live_bytes = 0, peak_bytes = 0;
+	int alloc_log = -1;
 	unsigned long long n_cuda_malloc = 0; // allocations that reached the driver (harcgpu_last_ms(ctx, "cudaMalloc_calls"))
-	static size_t round_bytes(size_t b) { return b <= (1u << 20) ? (b + 511) / 512 * 512 : (b + (2u << 20) - 1) / (2u << 20) * (2u << 20); }
+	// Size classes: eight per power of two (512-byte floor), so that a request whose size moves a little from pass to pass
+	// (the walk is not deterministic) lands in the class of the pass before, and a block serves requests of its own class
+	// or up to two classes below (<= 1.3x) -- small requests must not take the blocks that larger ones will ask for a
+	// moment later (an additive slack did that, and in a job on several GPUs, where every cudaMalloc also maps the block
+	// for the peers, each miss cost ~20 ms).
+	static size_t round_bytes(size_t b)
+	{
+		if (b <= 512) return 512;
+		size_t step = 64;
+		while ((step << 4) <= b) step <<= 1; // step = 2^(floor(log2 b) - 3)
+		return (b + step - 1) / step * step;
+	}
 	void trim()
 	{
 		for (auto &b : cached) cudaFree(b.p);
@@ -122,7 +137,7 @@ struct harcgpu_ctx {
 		size_t bytes = round_bytes((count ? count : 1) * sizeof(T));
 		size_t best = (size_t)-1;
 		for (size_t i = 0; i < cached.size(); i++)
-			if (cached[i].bytes >= bytes && cached[i].bytes <= bytes + bytes / 4 + (2u << 20) &&
+			if (cached[i].bytes >= bytes && cached[i].bytes <= bytes + bytes / 4 + bytes / 20 &&
 			    (best == (size_t)-1 || cached[i].bytes < cached[best].bytes))
 				best = i;
 		Block b;
@@ -134,6 +149,9 @@ struct harcgpu_ctx {
 		} else {
 			void *q = nullptr;
 			n_cuda_malloc++;
+			if (alloc_log < 0) { const char *ev = getenv("HARCGPU_ALLOC_LOG"); alloc_log = ev && atoi(ev) ? 1 : 0; }
+			if (alloc_log) fprintf(stderr, "[harcgpu dev %d] cudaMalloc #%llu of %zu bytes (%zu asked); %zu blocks / %zu MB cached\n", device, n_cuda_malloc,
+			                       bytes, (count ? count : 1) * sizeof(T), cached.size(), cached_bytes >> 20);
 			cudaError_t e = cudaMalloc(&q, bytes);
 			if (e != cudaSuccess) { // give the cached blocks back to the driver and try once more
 				cudaGetLastError();
@@ -207,8 +225,8 @@ void job_close(harcgpu_ctx *c);
 int job_barrier(harcgpu_ctx *c);
 // stage1.cu
 int s1_pack_reads(harcgpu_ctx *c, const void *d_ascii, u32 n);
-// pack n lines and store every packed read into `ndst` replicas (dst[r] points at the row of the first line)
-int s1_pack_reads_bcast(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *const *dst, int ndst);
+// pack n lines into out[n][NW]
+int s1_pack_reads_to(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *out);
 int s1_keys(harcgpu_ctx *c, const u64 *reads, u32 n, int words, int bitpos, int nbits, u32 id0, u64 *keys, u32 *ids);
 int s1_packN(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *out2, u64 *outN);
 struct DictShard { // where a dictionary shard of one job on several GPUs is built (inside the arena of ctx.h)

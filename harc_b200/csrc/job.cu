@@ -3,8 +3,9 @@
 // split (reorder.cpp:284-302 key extraction, 476-497 walker starts, encoder.cpp:169-180 contig ranges).
 //
 // What crosses NVLink, all of it by kernels of this library over peer memory (no library collective):
-//   * packed reads      -- every GPU packs its slice of the input and the pack kernel stores each packed read into all
-//                          replicas (stage1.cu: pack_kernel with a destination list): pack + all-gather in one kernel;
+//   * packed reads      -- every GPU packs its slice of the input and job_bcast_kernel stores the packed slice into the
+//                          replica of every other GPU, on a side stream next to the dictionary build (which only needs the
+//                          local slice): the all-gather of the packed reads, hidden behind the build;
 //   * (key, id) pairs   -- every GPU extracts the dictionary keys of its slice, cuts them by owner (one stable radix pass
 //                          over the shard bits) and job_push_kernel stores every range straight into the owner's receive
 //                          buffer at the offset that follows from the 8 x 8 count matrix (every GPU broadcasts its row):
@@ -126,6 +127,21 @@ __global__ void __launch_bounds__(256) job_pull_kernel(PullSrc src, uint4 *__res
 	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < seg_vec; i += gridDim.x * blockDim.x) to[i] = from[i];
 }
 
+// The all-gather of the packed reads: this GPU's slice goes into the replica of every other GPU (plain 16-byte stores into
+// NVLink peer memory).  Runs on a side stream next to the dictionary build, which only needs the local slice; the walk
+// is the first to need the whole replica.
+struct BcastDst { void *p[8]; };
+template <typename V> // uint4, or u64 when the slice does not start on a 16-byte boundary (odd words per read and odd base)
+__global__ void __launch_bounds__(512) job_bcast_kernel(const V *__restrict__ src, size_t nvec, BcastDst dst, int world, int me)
+{
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+		const V v = __ldg(&src[i]);
+		for (int r = 0; r < world; r++)
+			if (r != me) reinterpret_cast<V *>(dst.p[r])[i] = v;
+	}
+}
+
 size_t round256(size_t b) { return (b + 255) / 256 * 256; }
 JobHdr *hdr(harcgpu_ctx *c, int r) { return (JobHdr *)c->arena[r]; }
 HdrPtrs hdrs(harcgpu_ctx *c)
@@ -138,6 +154,8 @@ HdrPtrs hdrs(harcgpu_ctx *c)
 
 void job_close(harcgpu_ctx *c)
 {
+	if (c->st_bcast) cudaStreamSynchronize(c->st_bcast);
+	c->bcast_pending = false;
 	if (c->arena[c->shard_rank]) { c->reads = nullptr; c->n = 0; c->dicts_built = false; c->reordered = false; } // the reads lived in the arena
 	for (int r = 0; r < 8; r++) {
 		if (c->arena[r] && c->seg_opened[r]) cudaIpcCloseMemHandle(c->arena[r]);
@@ -166,6 +184,16 @@ int job_barrier(harcgpu_ctx *c)
 	c->job_epoch++;
 	job_barrier_kernel<<<KL + 1, 32, 0, c->st>>>(hdrs(c), c->shard_rank, c->shard_world, c->job_epoch, timeout_s * 1000000000ull);
 	CK(cudaGetLastError());
+	return 0;
+}
+
+// the compute stream goes on only after this GPU's broadcast of its slice is complete
+static int job_bcast_join(harcgpu_ctx *c)
+{
+	if (c->bcast_pending) {
+		CK(cudaStreamWaitEvent(c->st, c->ev_bcast, 0));
+		c->bcast_pending = false;
+	}
 	return 0;
 }
 
@@ -277,12 +305,31 @@ int harcgpu_job_load_reads_device(harcgpu_ctx *c, const void *d_ascii, uint32_t 
 		if (!c->arena[r]) { harcgpu_set_error("harcgpu_job_connect first"); return -1; }
 	for (int l = 0; l < 2; l++) if (!c->dicts_sharded) free_dict(c, c->d1[l]);
 	c->dicts_built = false; c->reordered = false; c->stream_set = false; c->pool_set = false; c->encoded = false;
-	if (job_barrier(c)) return -1; // nobody still reads the replicas of the pass before
+	if (job_bcast_join(c) || job_barrier(c)) return -1; // nobody still reads the replicas of the pass before
 	c->tic();
-	u64 *dst[8];
-	for (int r = 0; r < c->shard_world; r++) dst[r] = (u64 *)(c->arena[r] + c->arena_reads_off) + (size_t)c->job_base * c->NW;
-	if (s1_pack_reads_bcast(c, d_ascii, n_local, dst, c->shard_world)) return -1;
+	u64 *mine = (u64 *)(c->arena[c->shard_rank] + c->arena_reads_off) + (size_t)c->job_base * c->NW;
+	if (s1_pack_reads_to(c, d_ascii, n_local, mine)) return -1;
 	c->toc("pack");
+	if (c->shard_world > 1 && n_local) {
+		if (!c->st_bcast) {
+			CK(cudaStreamCreateWithFlags(&c->st_bcast, cudaStreamNonBlocking));
+			CK(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
+			CK(cudaEventCreateWithFlags(&c->ev_bcast, cudaEventDisableTiming));
+		}
+		CK(cudaEventRecord(c->ev_packed, c->st));
+		CK(cudaStreamWaitEvent(c->st_bcast, c->ev_packed, 0));
+		BcastDst dst;
+		for (int r = 0; r < 8; r++)
+			dst.p[r] = r < c->shard_world ? (void *)((u64 *)(c->arena[r] + c->arena_reads_off) + (size_t)c->job_base * c->NW) : nullptr;
+		const size_t words = (size_t)n_local * c->NW;
+		if (((uintptr_t)mine & 15) == 0 && words % 2 == 0)
+			job_bcast_kernel<uint4><<<KL + 74, 512, 0, c->st_bcast>>>((const uint4 *)mine, words / 2, dst, c->shard_world, c->shard_rank);
+		else
+			job_bcast_kernel<u64><<<KL + 74, 512, 0, c->st_bcast>>>((const u64 *)mine, words, dst, c->shard_world, c->shard_rank);
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(c->ev_bcast, c->st_bcast));
+		c->bcast_pending = true;
+	}
 	c->job_reads_loaded = true;
 	return 0;
 }
@@ -311,7 +358,7 @@ int harcgpu_job_build_dicts(harcgpu_ctx *c)
 	const int me = c->shard_rank, world = c->shard_world;
 	c->tic();
 	if (!c->dicts_sharded) {
-		if (job_barrier(c)) return -1; // every slice has arrived in this GPU's replica
+		if (job_bcast_join(c) || job_barrier(c)) return -1; // every slice has arrived in this GPU's replica
 		for (int l = 0; l < c->p.numdict; l++)
 			if (build_dict(c, c->d1[l], c->reads, nullptr, c->n, c->NW, c->p.dict_start[l], c->p.dict_end[l], 2, nullptr)) return -1;
 		c->toc("dict");
@@ -398,6 +445,7 @@ int harcgpu_job_reorder(harcgpu_ctx *c)
 	if (!c || !c->arena[c->shard_rank] || !c->dicts_built) { harcgpu_set_error("harcgpu_job_build_dicts first"); return -1; }
 	CK(cudaSetDevice(c->device));
 	if (c->shard_world > 1) {
+		if (job_bcast_join(c)) return -1; // this GPU's slice has reached every replica before it says so at the barrier
 		const u64 lo = std::min<u64>((u64)c->shard_rank * c->seg_per, c->shard_n), hi = std::min<u64>(lo + c->seg_per, c->shard_n);
 		CK(cudaMemsetAsync(c->seg[c->shard_rank], 0, (size_t)c->seg_per / 8, c->st));
 		if (s1_init_claim(c, c->seg[c->shard_rank], (u32)(hi - lo))) return -1;

@@ -33,11 +33,8 @@ __device__ __forceinline__ u32 codes4(u32 w)
 // four at a time from aligned 32-bit shared-memory words (funnel shift for the line's byte offset).
 // WITH_N (stage II pool, encoder.cpp:731-745): 'N' is stored as code 0 and flagged in a second word array at the
 // low bit of the base's pair; the reference's 3-bit code is then 2*code2 + nflag.
-// One job on several GPUs: the packed reads are stored into every GPU's replica by the kernel that produces them (plain
-// stores into NVLink peer memory; the pack and the all-gather of the packed reads are one kernel).
-struct PackDst { u64 *p[8]; int n; };
 template <bool WITH_N>
-__global__ void __launch_bounds__(256) pack_kernel(const char *__restrict__ ascii, u32 n, int L, int NWo, PackDst dst,
+__global__ void __launch_bounds__(256) pack_kernel(const char *__restrict__ ascii, u32 n, int L, int NWo, u64 *__restrict__ out,
                                                    u64 *__restrict__ outN)
 {
 	extern __shared__ uint4 stage4[];
@@ -93,7 +90,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const char *__restrict__ asci
 			v |= (u64)squeeze4(c) << (8 * i);
 		}
 		const u64 m = lowmask(2 * nb);
-		for (int d = 0; d < dst.n; d++) dst.p[d][(r0 + r) * NWo + k] = v & m;
+		out[(r0 + r) * NWo + k] = v & m;
 		if (WITH_N) outN[(r0 + r) * NWo + k] = vn & m;
 	}
 }
@@ -271,21 +268,14 @@ int s1_pack_reads(harcgpu_ctx *c, const void *d_ascii, u32 n)
 	if (n == 0) return 0;
 	size_t smem = (size_t)PACK_RPB * (c->L + 1);
 	smem = (smem + 15) / 16 * 16 + 48; // slack: the last word of the last line reads up to 35 bytes past its start
-	PackDst dst;
-	dst.n = 1; dst.p[0] = c->reads;
-	pack_kernel<false><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, dst, nullptr);
-	CK(cudaGetLastError());
-	return 0;
+	return s1_pack_reads_to(c, d_ascii, n, c->reads);
 }
-int s1_pack_reads_bcast(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *const *out, int ndst)
+int s1_pack_reads_to(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *out)
 {
 	if (n == 0) return 0;
 	size_t smem = (size_t)PACK_RPB * (c->L + 1);
 	smem = (smem + 15) / 16 * 16 + 48;
-	PackDst dst;
-	dst.n = ndst;
-	for (int d = 0; d < 8; d++) dst.p[d] = d < ndst ? out[d] : nullptr;
-	pack_kernel<false><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, dst, nullptr);
+	pack_kernel<false><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, out, nullptr);
 	CK(cudaGetLastError());
 	return 0;
 }
@@ -302,10 +292,8 @@ int s1_packN(harcgpu_ctx *c, const void *d_ascii, u32 n, u64 *out2, u64 *outN)
 	if (n == 0) return 0;
 	size_t smem = (size_t)PACK_RPB * (c->L + 1);
 	smem = (smem + 15) / 16 * 16 + 48; // slack: the last word of the last line reads up to 35 bytes past its start
-	PackDst dst;
-	dst.n = 1; dst.p[0] = out2;
-	if (outN) pack_kernel<true><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, dst, outN);
-	else pack_kernel<false><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, dst, nullptr);
+	if (outN) pack_kernel<true><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, out2, outN);
+	else pack_kernel<false><<<KL + cdiv(n, PACK_RPB), 256, smem, c->st>>>((const char *)d_ascii, n, c->L, c->NW, out2, nullptr);
 	CK(cudaGetLastError());
 	return 0;
 }

@@ -87,6 +87,7 @@ struct alignas(16) WalkerSmem {
 	u32 chunk, fill, seq;                      // forward log
 	u32 lchunk, lfill, lfirst, lcount, j1;     // left log
 	u32 pend, pend_f;                          // left run: read found last, not yet written
+	u32 cnt[4];                                // counters that change rarely live here, not in registers: steps, restarts, harvested, lost claims
 	u32 ref[2 * NW];      // consensus of the current window, 2 bits/base (reorder.cpp:466)
 	u32 zpad[NW];
 	u32 rref[2 * NW];     // its reverse complement
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 	if (sub < 2) { s.zpad2[sub] = 0u; s.zpad3[sub] = 0u; }
 	__syncthreads();
 
-	u32 c_steps = 0, c_probes = 0, c_hits = 0, c_cmp = 0, c_fail = 0, c_restart = 0, c_harvest = 0;
+	u32 c_probes = 0, c_hits = 0, c_cmp = 0;
 #ifdef WALK_PROF
 	u64 pacc[16];
 	for (int i = 0; i < 16; i++) pacc[i] = 0;
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 		if (s.fill == CHUNK) {
 			if (s.chunk != NONE) a.chunk_fill[s.chunk] = CHUNK;
 			u32 c = atomicAdd(a.chunk_ctr, 1u);
-			if (c >= a.max_chunks) c = a.max_chunks - 1; // cannot happen: max_chunks = n/CHUNK + walkers + 1
+			if (c >= a.max_chunks) c = a.max_chunks - 1; // overflow (the host sees the counter and fails): keep the stores in bounds
 			a.chunk_key[c] = ((u64)wid << 32) | s.seq++;
 			s.chunk = c;
 			s.fill = 0;
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 	auto lemit = [&](u64 rec) {
 		if (s.lchunk == NONE || s.lfill == CHUNK) {
 			u32 c = atomicAdd(a.lchunk_ctr, 1u);
-			if (c >= a.max_lchunks) c = a.max_lchunks - 1; // cannot happen: max_lchunks = n/CHUNK + walkers + 1
+			if (c >= a.max_lchunks) c = a.max_lchunks - 1; // overflow (the host sees the counter and fails): keep the stores in bounds
 			a.lprev[c] = s.lchunk;
 			if (s.lfirst == NONE) s.lfirst = c;
 			s.lchunk = c;
@@ -336,6 +337,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 		s.chunk = NONE; s.fill = CHUNK; s.seq = 0;
 		s.lchunk = NONE; s.lfill = 0; s.lfirst = NONE; s.lcount = 0; s.j1 = 0; s.pend = 0; s.pend_f = 0;
 		s.stripe = wid; s.stripes_tried = 0;
+		s.cnt[0] = s.cnt[1] = s.cnt[2] = s.cnt[3] = 0u;
 		s.cursor = wid < a.walkers ? (long long)((((u64)wid + 1) * a.n_loc) / a.walkers) - 1 : -1;
 	}
 	__syncwarp(gmask);
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 		const u32 start = a.base + (u32)((u64)wid * (a.n_loc / a.walkers));
 		int ok = leader ? (int)try_claim(a, start) : 0;
 		ok = __shfl_sync(gmask, ok, gbase);
-		if (ok) { current = start; state = S_NEWHEAD; c_restart += leader; }
+		if (ok) { current = start; state = S_NEWHEAD; if (leader) s.cnt[1]++; }
 		else state = S_RESTART;
 	}
 
@@ -470,7 +472,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 				if (got) { current = a.base + j; got_head = true; break; }
 			}
 			if (leader) { s.stripe = stripe; s.stripes_tried = tried; s.cursor = cursor; }
-			if (got_head) { state = S_NEWHEAD; c_restart += leader; }
+			if (got_head) { state = S_NEWHEAD; if (leader) s.cnt[1]++; }
 			else {
 				state = S_DONE;
 				if (leader && s.chunk != NONE) a.chunk_fill[s.chunk] = s.fill;
@@ -503,7 +505,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 			const int j = jb + jq;
 			issue(j, pc);
 			if (jb > 0) prefetch(j + SPR);
-			c_steps += leader && jb == 0;
+			if (leader && jb == 0) s.cnt[0]++;
 			PROF_CNT(8, 1);
 			PROF_CNT(9, jb == 0);
 
@@ -599,7 +601,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 						int got = 0;
 						if (sub == win) {
 							got = try_claim(a, cand);
-							if (!got) { c_fail++; ps = P_BIN; }
+							if (!got) { atomicAdd(&s.cnt[3], 1u); ps = P_BIN; }
 						}
 						got = __shfl_sync(gmask, got, gbase + win);
 						if (!got) { win = G; continue; }
@@ -629,7 +631,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 				const u32 grp = __match_any_sync(gmask, mine ? (u64)cand : ((1ull << 32) | (u64)lane)); // lanes that hold the same read
 				const bool first_of_grp = mine && (__ffs(grp) - 1) == lane;
 				int got = 0;
-				if (first_of_grp) { got = try_claim(a, cand); if (!got) c_fail++; }
+				if (first_of_grp) { got = try_claim(a, cand); if (!got) atomicAdd(&s.cnt[3], 1u); }
 				bh = __ballot_sync(gmask, got != 0) >> gbase;
 				if (mine && !got) ps = P_BIN; // lost (or the same read as a lane in front): on with the bin if the round goes on
 				if (!bh) { win = G; continue; } // every claim of the wave was lost to other walkers
@@ -687,7 +689,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 					}
 					append(rid2, (w2 >> 2) - last_rel, (w2 & 3) >= 2, bh == 0);
 					last_rel = w2 >> 2;
-					c_harvest += leader;
+					if (leader) s.cnt[2]++;
 				}
 				dry = 0;
 				jb = 0;
@@ -761,18 +763,15 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 #endif
 	// counters
 	for (int o = 16; o > 0; o >>= 1) {
-		c_steps += __shfl_xor_sync(FULL, c_steps, o);
 		c_probes += __shfl_xor_sync(FULL, c_probes, o);
 		c_hits += __shfl_xor_sync(FULL, c_hits, o);
 		c_cmp += __shfl_xor_sync(FULL, c_cmp, o);
-		c_fail += __shfl_xor_sync(FULL, c_fail, o);
-		c_restart += __shfl_xor_sync(FULL, c_restart, o);
-		c_harvest += __shfl_xor_sync(FULL, c_harvest, o);
 	}
-	if (lane == 0) {
-		atomicAdd(&a.counters[0], (u64)c_steps); atomicAdd(&a.counters[1], (u64)c_probes); atomicAdd(&a.counters[2], (u64)c_hits);
-		atomicAdd(&a.counters[3], (u64)c_cmp); atomicAdd(&a.counters[4], (u64)c_fail); atomicAdd(&a.counters[5], (u64)c_restart);
-		atomicAdd(&a.counters[6], (u64)c_harvest);
+	__syncwarp();
+	if (lane == 0) { atomicAdd(&a.counters[1], (u64)c_probes); atomicAdd(&a.counters[2], (u64)c_hits); atomicAdd(&a.counters[3], (u64)c_cmp); }
+	if (leader) {
+		atomicAdd(&a.counters[0], (u64)s.cnt[0]); atomicAdd(&a.counters[5], (u64)s.cnt[1]); atomicAdd(&a.counters[6], (u64)s.cnt[2]);
+		atomicAdd(&a.counters[4], (u64)s.cnt[3]);
 	}
 }
 
@@ -898,10 +897,13 @@ int s1_reorder(harcgpu_ctx *c)
 	c->release(c->order); c->release(c->order_s); c->release(c->rev); c->release(c->flag); c->release(c->pos);
 	c->order = c->order_s = nullptr; c->rev = c->flag = c->pos = nullptr;
 	c->n_matched = c->n_single = c->n_unmatched = 0;
-	if (c->alloc(&c->order, n) || c->alloc(&c->order_s, n) || c->alloc(&c->rev, n) || c->alloc(&c->flag, n) || c->alloc(&c->pos, n))
-		return -1;
 	CK(cudaMemsetAsync(c->counters, 0, 8 * sizeof(u64), st));
-	if (n == 0) { c->reordered = true; c->ms["walk"] = 0; c->ms["finalize"] = 0; return 0; }
+	auto no_reads = [&]() { // empty streams (the getters and stage II take null arrays of zero entries, but keep them valid)
+		if (c->alloc(&c->order, 1) || c->alloc(&c->order_s, 1) || c->alloc(&c->rev, 1) || c->alloc(&c->flag, 1) || c->alloc(&c->pos, 1)) return -1;
+		c->reordered = true; c->ms["walk"] = 0; c->ms["finalize"] = 0;
+		return 0;
+	};
+	if (n == 0) return no_reads();
 
 	// walkers: the reference's num_thr.  Auto: one walker per reads_per_walker reads (every extra walker costs chain
 	// heads), capped at what is resident at once.
@@ -928,12 +930,15 @@ int s1_reorder(harcgpu_ctx *c)
 	const u32 per = c->p.reads_per_walker > 0 ? (u32)c->p.reads_per_walker : 4096u;
 	u32 walkers = c->p.walkers > 0 ? (u32)c->p.walkers : (u32)std::min<u64>(resident, std::max<u64>(1, n_loc / per));
 	if (walkers > n_loc) walkers = n_loc;
-	if (walkers == 0) { c->reordered = true; c->ms["walk"] = 0; c->ms["finalize"] = 0; return 0; } // no read in this GPU's range
+	if (walkers == 0) return no_reads(); // no read in this GPU's range
 	c->walkers_used = walkers;
 	// left extension: off for a single walker unless asked for (one walker without it = the reference at num_thr=1)
 	const int extend = c->p.extend > 0 ? 1 : (c->p.extend < 0 ? 0 : (walkers > 1 ? 1 : 0));
 
-	u32 max_chunks = n / CHUNK + walkers + 1;
+	// Room of the record logs: every read once.  One job on several GPUs: a GPU's walkers may claim any read, but the GPUs
+	// advance side by side, so twice its share (+ slack) is reserved instead of the whole job; running over is detected.
+	const u64 cap_reads = sharded ? std::min<u64>(n, 2 * (((u64)n + c->shard_world - 1) / c->shard_world) + (1u << 20)) : n;
+	u32 max_chunks = (u32)(cap_reads / CHUNK) + walkers + 1;
 	u64 *recs = nullptr, *chunk_key = nullptr, *key_sorted = nullptr, *scan_tmp = nullptr, *lrecs = nullptr;
 	u32 *chunk_fill = nullptr, *ctrs = nullptr, *chunk_id = nullptr, *chunk_sorted = nullptr, *cm = nullptr, *cs = nullptr,
 	    *om = nullptr, *os = nullptr, *totals = nullptr, *lprev = nullptr;
@@ -1019,10 +1024,14 @@ int s1_reorder(harcgpu_ctx *c)
 
 	// ---- finalize
 	c->tic();
-	u32 nchunks = 0;
-	CK(cudaMemcpyAsync(&nchunks, ctrs, 4, cudaMemcpyDeviceToHost, st));
+	u32 hctr[2] = { 0, 0 };
+	CK(cudaMemcpyAsync(hctr, ctrs, 8, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
-	if (nchunks > max_chunks) { harcgpu_set_error("record log overflow"); return -1; }
+	const u32 nchunks = hctr[0], nlchunks = hctr[1];
+	if (nchunks > max_chunks || nlchunks > max_chunks) {
+		harcgpu_set_error("record log overflow: this GPU's walkers claimed more than %llu reads (its share of the job twice over)", (unsigned long long)cap_reads);
+		return -1;
+	}
 	if (c->alloc(&key_sorted, nchunks) || c->alloc(&chunk_id, nchunks) || c->alloc(&chunk_sorted, nchunks) || c->alloc(&cm, nchunks) ||
 	    c->alloc(&cs, nchunks) || c->alloc(&om, nchunks) || c->alloc(&os, nchunks) || c->alloc(&totals, 2) ||
 	    c->alloc(&scan_tmp, scan_tmp_elems(nchunks)))
@@ -1042,13 +1051,17 @@ int s1_reorder(harcgpu_ctx *c)
 	CK(cudaGetLastError());
 	if (exclusive_scan_u32(cm, om, nchunks, scan_tmp, totals, st)) return -1;
 	if (exclusive_scan_u32(cs, os, nchunks, scan_tmp, totals + 1, st)) return -1;
-	chunk_gather_kernel<<<KL + cdiv((size_t)nchunks * 32, 256), 256, 0, st>>>(recs, chunk_sorted, chunk_fill, nchunks, om, os, c->order,
-	                                                                      c->rev, c->flag, c->pos, c->order_s);
-	CK(cudaGetLastError());
 	u32 tot[2];
 	CK(cudaMemcpyAsync(tot, totals, 8, cudaMemcpyDeviceToHost, st));
 	u64 cnt[8];
 	CK(cudaMemcpyAsync(cnt, c->counters, 64, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	// the five streams, at their exact sizes
+	if (c->alloc(&c->order, tot[0]) || c->alloc(&c->order_s, tot[1]) || c->alloc(&c->rev, tot[0]) || c->alloc(&c->flag, tot[0]) || c->alloc(&c->pos, tot[0]))
+		return -1;
+	chunk_gather_kernel<<<KL + cdiv((size_t)nchunks * 32, 256), 256, 0, st>>>(recs, chunk_sorted, chunk_fill, nchunks, om, os, c->order,
+	                                                                      c->rev, c->flag, c->pos, c->order_s);
+	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(st));
 	c->toc("finalize");
 	c->n_matched = tot[0]; c->n_single = tot[1]; c->n_unmatched = (u32)cnt[5];

@@ -30,8 +30,8 @@ def _ref_size(d, L, T):
 @pytest.mark.parametrize("case", SIZE_CASES, ids=[c[0] for c in SIZE_CASES])
 def test_compressed_size_within_2_percent_of_reference(workroot, case):
     """North star: 'the reorder itself is held to compressed bits/base within 2 % of the reference run with -t 1 and
-    -t 8'.  The reference's two runs differ from each other by up to 3.4 % on noisy data, so the bound
-    is taken against the larger of the two and both ratios are printed."""
+    -t 8'.  The bound is asserted against BOTH runs (the reference's two runs differ from each other by up to 3.4 % on
+    noisy data; ours has to stay within 2 % of the smaller one as well) and both ratios are printed."""
     import harc_b200
     name, n, L, G, rc, err = case
     d = H.make_dataset(workroot, name, n, L, G, rc, err, seed=21)
@@ -45,7 +45,7 @@ def test_compressed_size_within_2_percent_of_reference(workroot, case):
     bpb = lambda s: 8.0 * s / (n * L)
     print(json.dumps({"case": name, "bits_per_base": {"gpu": bpb(sg), "ref_t1": bpb(s1), "ref_t8": bpb(s8)},
                       "gpu_over_ref_t1": sg / s1, "gpu_over_ref_t8": sg / s8}))
-    assert sg <= 1.02 * max(s1, s8), (sg, s1, s8)
+    assert sg <= 1.02 * s1 and sg <= 1.02 * s8, (sg, s1, s8)
     # and the archive is lossless through the reference decoder
     R.decoder(g)
     fq = np.fromfile(os.path.join(d, "r.fastq"), dtype=np.uint8).tobytes().split(b"\n")[1::4]

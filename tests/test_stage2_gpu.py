@@ -131,7 +131,7 @@ def test_pipeline_lossless_through_reference_decoder(gpu, workroot, case):
 def test_in_memory_handoff_equals_file_path(gpu, workroot):
     """reorder -> encode on one context (streams stay on the device) == reorder_dir -> encode_dir through files."""
     name, n, L, G, rc, err = CASES[0]
-    d = H.dataset(workroot, case, seed=11)
+    d = H.dataset(workroot, CASES[0], seed=11)
     g = H.clone(d, d + ".mem")
     out = os.path.join(g, "output")
     ctx = gpu.HarcGpu(L, walkers=1, file_sets=2)
