@@ -32,6 +32,8 @@ struct harcgpu_ctx {
 	DictDev d1[2];
 	bool dicts_built = false;
 	u32 *claim = nullptr;   // bitmap, 1 = still unclaimed (remainingreads, reorder.cpp:449)
+	u32 *bloom1 = nullptr;  // blocked Bloom filter over the keys of both stage I dictionaries, sized to stay in L2 (job.cu: job_bloom_pos)
+	u32 bloom1_words = 0;
 	long long *gpos = nullptr;
 	u64 *counters = nullptr; // 8 x u64
 	u32 walkers_used = 0;
@@ -221,6 +223,7 @@ int ing_unpack_clean(harcgpu_ctx *c, char *d_out);
 // walk.cu
 int s1_init_claim(harcgpu_ctx *c, u32 *claim, u32 n);
 // job.cu
+int job_bloom_insert(harcgpu_ctx *c, const u64 *mixed_keys, u32 nk, int l, int world, u32 seg_words, u32 *bloom);
 void job_close(harcgpu_ctx *c);
 int job_barrier(harcgpu_ctx *c);
 // stage1.cu

@@ -152,6 +152,14 @@ HdrPtrs hdrs(harcgpu_ctx *c)
 }
 } // namespace
 
+int job_bloom_insert(harcgpu_ctx *c, const u64 *mixed_keys, u32 nk, int l, int world, u32 seg_words, u32 *bloom)
+{
+	if (!nk) return 0;
+	job_bloom_insert_kernel<<<KL + cdiv(nk, 256), 256, 0, c->st>>>(mixed_keys, nk, l, world, seg_words, bloom);
+	CK(cudaGetLastError());
+	return 0;
+}
+
 void job_close(harcgpu_ctx *c)
 {
 	if (c->st_bcast) cudaStreamSynchronize(c->st_bcast);

@@ -391,11 +391,12 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 		if (p.pend) {
 			probe_key(j, p.key, p.h);
 			c_probes++;
-			if (dv.world && a.bloom) {
-				// the table of this key lives on another GPU (world - 1 times out of world): ask the local filter first, most
-				// window keys are in no dictionary and then nothing crosses NVLink
+			if (a.bloom) {
+				// most window keys are in no dictionary: ask the filter first (one job on several GPUs: the table of the key lives
+				// on another GPU world - 1 times out of world, and then nothing crosses NVLink; one GPU: the filter sits in L2
+				// and the tables in HBM)
 				u32 bw, bb;
-				job_bloom_pos(p.key, l, dv.world, a.bloom_seg_words, bw, bb);
+				job_bloom_pos(p.key, l, dv.world ? dv.world : 1, a.bloom_seg_words, bw, bb);
 				if ((__ldg(&a.bloom[bw]) & bb) != bb) { p.pend = false; return; }
 			}
 			const ulonglong2 *sl = slots_of(p.key);
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 
 	// L2 prefetch of the bucket that the probe for shift j will read (used one round ahead in a fruitless search)
 	auto prefetch = [&](int j) {
-		if (!dv.world && ((vmask >> (j >> SPR_LOG)) & 1u)) {
+		if (!dv.world && !a.bloom && ((vmask >> (j >> SPR_LOG)) & 1u)) {
 			u64 key;
 			u32 h;
 			probe_key(j, key, h);
@@ -974,6 +975,7 @@ int s1_reorder(harcgpu_ctx *c)
 	}
 	a.bloom = c->dicts_sharded && c->job_bloom ? (const u32 *)(c->arena[c->shard_rank] + c->arena_bloom_off) : nullptr;
 	a.bloom_seg_words = c->bloom_seg_words;
+	if (!c->dicts_sharded && !sharded && c->bloom1) { a.bloom = c->bloom1; a.bloom_seg_words = c->bloom1_words; }
 	a.claim = sharded ? c->seg[c->shard_rank] : c->claim; a.hint = c->claim; a.stripe_done = stripe_done; a.walkers = walkers;
 	for (int r = 0; r < 8; r++) a.seg[r] = sharded && r < c->shard_world ? c->seg[r] : nullptr;
 	a.seg_per = sharded ? c->seg_per : 0u; a.base = base; a.n_loc = n_loc; a.world = sharded ? c->shard_world : 1;
@@ -984,14 +986,15 @@ int s1_reorder(harcgpu_ctx *c)
 	// tuning aid: keep the claim bitmap (1 bit per read, hit by every candidate test and claim) in the persisting part of L2
 	bool l2win = false;
 	if (const char *e = getenv("HARCGPU_L2PERSIST")) {
-		const size_t want = ((size_t)n + 31) / 32 * 4;
+		const bool pin_bloom = c->bloom1 && a.bloom == c->bloom1; // the filter rather than the claim bitmap if there is one
+		const size_t want = pin_bloom ? (size_t)c->bloom1_words * 4 : ((size_t)n + 31) / 32 * 4;
 		int maxwin = 0;
 		CK(cudaDeviceGetAttribute(&maxwin, cudaDevAttrMaxAccessPolicyWindowSize, c->device));
 		if (atoi(e) > 0 && !sharded && want <= (size_t)maxwin) {
 			CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(want * 2, (size_t)atoi(e) << 20)));
 			cudaStreamAttrValue av;
 			memset(&av, 0, sizeof av);
-			av.accessPolicyWindow.base_ptr = c->claim;
+			av.accessPolicyWindow.base_ptr = pin_bloom ? (void *)c->bloom1 : (void *)c->claim;
 			av.accessPolicyWindow.num_bytes = want;
 			av.accessPolicyWindow.hitRatio = 1.0f;
 			av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
