@@ -473,7 +473,7 @@ def run_single(args, rank, world, local, dist, json_fd):
         return
 
     out = {
-        "metric": METRIC, "value": value, "unit": "Mreads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC if L == 100 else METRIC.replace("100bp", "%dbp" % L), "value": value, "unit": "Mreads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": cfg["name"] + (", per GPU" if world > 1 else ""), "workload_signature": workload_signature(cfg, args.seed),
                    "reads_per_gpu": cfg["reads"], "clean_reads": n_clean, "reads_with_N": n_N, "walkers": ctx.p.walkers or "auto",
@@ -591,6 +591,9 @@ def run_one_job(args, rank, world, local, dist, json_fd):
         l0 = harc_b200.launch_count()
         m0 = ctx.last_ms("cudaMalloc_calls")
         ev[0].record(stream)
+        if os.environ.get("HARCGPU_ALLOC_LOG"):
+            sys.stderr.write("=== rank %d: timed region (%s) starts\n" % (rank, tag))
+            sys.stderr.flush()
         for k in range(steps):
             fn()
             ev[k + 1].record(stream)

@@ -32,6 +32,7 @@ struct harcgpu_ctx {
 	DictDev d1[2];
 	bool dicts_built = false;
 	u32 *claim = nullptr;   // bitmap, 1 = still unclaimed (remainingreads, reorder.cpp:449)
+	unsigned long long *tailc = nullptr; // cursor cache of the big bins (walk.cu: advance)
 	u32 *bloom1 = nullptr;  // blocked Bloom filter over the keys of both stage I dictionaries, sized to stay in L2 (job.cu: job_bloom_pos)
 	u32 bloom1_words = 0;
 	long long *gpos = nullptr;
@@ -61,7 +62,7 @@ struct harcgpu_ctx {
 	bool shard_ready = false, job_reads_loaded = false;
 	cudaStream_t st_bcast = nullptr;      // side stream of the broadcast of this GPU's packed slice
 	cudaEvent_t ev_packed = nullptr, ev_bcast = nullptr;
-	bool bcast_pending = false;
+	bool bcast_pending = false, bcast_needed = false;
 	int (*pool_exchange)(void *user, void *d_best, uint64_t count) = nullptr;
 	void *pool_exchange_user = nullptr;
 	int (*job_barrier_hook)(void *user) = nullptr; // ranks that share one GPU (tests): host barrier instead of the barrier kernel

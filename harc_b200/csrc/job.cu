@@ -195,9 +195,40 @@ int job_barrier(harcgpu_ctx *c)
 	return 0;
 }
 
+// starts the broadcast of this GPU's packed slice on the side stream (behind everything queued on the compute stream so far)
+static int job_bcast_start(harcgpu_ctx *c)
+{
+	if (!c->bcast_needed) return 0;
+	c->bcast_needed = false;
+	const u32 n_local = c->job_nloc;
+	u64 *mine = (u64 *)(c->arena[c->shard_rank] + c->arena_reads_off) + (size_t)c->job_base * c->NW;
+	{
+		if (!c->st_bcast) {
+			CK(cudaStreamCreateWithFlags(&c->st_bcast, cudaStreamNonBlocking));
+			CK(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
+			CK(cudaEventCreateWithFlags(&c->ev_bcast, cudaEventDisableTiming));
+		}
+		CK(cudaEventRecord(c->ev_packed, c->st));
+		CK(cudaStreamWaitEvent(c->st_bcast, c->ev_packed, 0));
+		BcastDst dst;
+		for (int r = 0; r < 8; r++)
+			dst.p[r] = r < c->shard_world ? (void *)((u64 *)(c->arena[r] + c->arena_reads_off) + (size_t)c->job_base * c->NW) : nullptr;
+		const size_t words = (size_t)n_local * c->NW;
+		if (((uintptr_t)mine & 15) == 0 && words % 2 == 0)
+			job_bcast_kernel<uint4><<<KL + 74, 512, 0, c->st_bcast>>>((const uint4 *)mine, words / 2, dst, c->shard_world, c->shard_rank);
+		else
+			job_bcast_kernel<u64><<<KL + 74, 512, 0, c->st_bcast>>>((const u64 *)mine, words, dst, c->shard_world, c->shard_rank);
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(c->ev_bcast, c->st_bcast));
+		c->bcast_pending = true;
+	}
+	return 0;
+}
+
 // the compute stream goes on only after this GPU's broadcast of its slice is complete
 static int job_bcast_join(harcgpu_ctx *c)
 {
+	if (job_bcast_start(c)) return -1; // (not started yet: a caller that skipped the dictionary build)
 	if (c->bcast_pending) {
 		CK(cudaStreamWaitEvent(c->st, c->ev_bcast, 0));
 		c->bcast_pending = false;
@@ -318,26 +349,7 @@ int harcgpu_job_load_reads_device(harcgpu_ctx *c, const void *d_ascii, uint32_t 
 	u64 *mine = (u64 *)(c->arena[c->shard_rank] + c->arena_reads_off) + (size_t)c->job_base * c->NW;
 	if (s1_pack_reads_to(c, d_ascii, n_local, mine)) return -1;
 	c->toc("pack");
-	if (c->shard_world > 1 && n_local) {
-		if (!c->st_bcast) {
-			CK(cudaStreamCreateWithFlags(&c->st_bcast, cudaStreamNonBlocking));
-			CK(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
-			CK(cudaEventCreateWithFlags(&c->ev_bcast, cudaEventDisableTiming));
-		}
-		CK(cudaEventRecord(c->ev_packed, c->st));
-		CK(cudaStreamWaitEvent(c->st_bcast, c->ev_packed, 0));
-		BcastDst dst;
-		for (int r = 0; r < 8; r++)
-			dst.p[r] = r < c->shard_world ? (void *)((u64 *)(c->arena[r] + c->arena_reads_off) + (size_t)c->job_base * c->NW) : nullptr;
-		const size_t words = (size_t)n_local * c->NW;
-		if (((uintptr_t)mine & 15) == 0 && words % 2 == 0)
-			job_bcast_kernel<uint4><<<KL + 74, 512, 0, c->st_bcast>>>((const uint4 *)mine, words / 2, dst, c->shard_world, c->shard_rank);
-		else
-			job_bcast_kernel<u64><<<KL + 74, 512, 0, c->st_bcast>>>((const u64 *)mine, words, dst, c->shard_world, c->shard_rank);
-		CK(cudaGetLastError());
-		CK(cudaEventRecord(c->ev_bcast, c->st_bcast));
-		c->bcast_pending = true;
-	}
+	c->bcast_needed = c->shard_world > 1 && n_local;
 	c->job_reads_loaded = true;
 	return 0;
 }
@@ -366,7 +378,7 @@ int harcgpu_job_build_dicts(harcgpu_ctx *c)
 	const int me = c->shard_rank, world = c->shard_world;
 	c->tic();
 	if (!c->dicts_sharded) {
-		if (job_bcast_join(c) || job_barrier(c)) return -1; // every slice has arrived in this GPU's replica
+		if (job_bcast_start(c) || job_bcast_join(c) || job_barrier(c)) return -1; // every slice has arrived in this GPU's replica
 		for (int l = 0; l < c->p.numdict; l++)
 			if (build_dict(c, c->d1[l], c->reads, nullptr, c->n, c->NW, c->p.dict_start[l], c->p.dict_end[l], 2, nullptr)) return -1;
 		c->toc("dict");
@@ -402,6 +414,9 @@ int harcgpu_job_build_dicts(harcgpu_ctx *c)
 		CK(cudaGetLastError());
 	}
 	c->lap("dict_push");
+	// the pairs are on their way: now the packed slice follows, on the side stream, under the shard build (the pairs go
+	// first because the build waits for them, while the replicas are only needed by the walk)
+	if (job_bcast_start(c)) return -1;
 	if (job_barrier(c)) return -1; // every pair has arrived
 	c->lap("dict_barrier2");
 	JobHdr h;
@@ -457,7 +472,8 @@ int harcgpu_job_reorder(harcgpu_ctx *c)
 		const u64 lo = std::min<u64>((u64)c->shard_rank * c->seg_per, c->shard_n), hi = std::min<u64>(lo + c->seg_per, c->shard_n);
 		CK(cudaMemsetAsync(c->seg[c->shard_rank], 0, (size_t)c->seg_per / 8, c->st));
 		if (s1_init_claim(c, c->seg[c->shard_rank], (u32)(hi - lo))) return -1;
-		if (job_barrier(c)) return -1; // every range of the bitmap is armed before any walker claims
+		// (the barrier "every range of the bitmap is armed before any walker claims" is inside s1_reorder, right in front of
+		// the walk kernel)
 	}
 	c->shard_ready = true;
 	if (s1_reorder(c)) return -1;

@@ -931,7 +931,10 @@ int s1_reorder(harcgpu_ctx *c)
 	const u32 per = c->p.reads_per_walker > 0 ? (u32)c->p.reads_per_walker : 4096u;
 	u32 walkers = c->p.walkers > 0 ? (u32)c->p.walkers : (u32)std::min<u64>(resident, std::max<u64>(1, n_loc / per));
 	if (walkers > n_loc) walkers = n_loc;
-	if (walkers == 0) return no_reads(); // no read in this GPU's range
+	if (walkers == 0) { // no read in this GPU's range: it still meets the others where they start their walks
+		if (sharded && job_barrier(c)) return -1;
+		return no_reads();
+	}
 	c->walkers_used = walkers;
 	// left extension: off for a single walker unless asked for (one walker without it = the reference at num_thr=1)
 	const int extend = c->p.extend > 0 ? 1 : (c->p.extend < 0 ? 0 : (walkers > 1 ? 1 : 0));
@@ -954,8 +957,9 @@ int s1_reorder(harcgpu_ctx *c)
 	init_claim_kernel<<<KL + cdiv((n + 31) / 32, 256), 256, 0, st>>>(c->claim, n);
 	CK(cudaGetLastError());
 	u32 *stripe_done = nullptr;
-	unsigned long long *tailc = nullptr;
-	if (c->alloc(&stripe_done, walkers) || c->alloc(&tailc, TAILC_ENTRIES)) return -1;
+	if (!c->tailc && c->alloc(&c->tailc, TAILC_ENTRIES)) return -1; // kept for the life of the context
+	unsigned long long *tailc = c->tailc;
+	if (c->alloc(&stripe_done, walkers)) return -1;
 	CK(cudaMemsetAsync(stripe_done, 0, 4 * (size_t)walkers, st));
 	CK(cudaMemsetAsync(tailc, 0xff, 8 * (size_t)TAILC_ENTRIES, st)); // no bin has this tag
 
@@ -1003,6 +1007,11 @@ int s1_reorder(harcgpu_ctx *c)
 			l2win = true;
 		}
 	}
+	// One job on several GPUs: the GPUs meet HERE, with every allocation and memset of this call behind them, so that all
+	// walk kernels start within microseconds of one another.  (A GPU that starts late -- one cudaMalloc is ~20 ms when the
+	// block has to be mapped for the peers -- finds most reads claimed, ends up with a small share, and the sizes of
+	// everything downstream change from pass to pass.)  Every range of the bitmap was armed before this call.
+	if (sharded && job_barrier(c)) return -1;
 	c->tic();
 	DISPATCH_NW_G(c->NW, lanes, (rc = launch_walk<NW, G>(c, a)));
 	if (rc) return rc;
