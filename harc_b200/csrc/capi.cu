@@ -77,11 +77,18 @@ int harcgpu_create(int device, const harcgpu_params *p, harcgpu_ctx **out)
 	c->NW = (2 * c->L + 63) / 64;
 	c->NW3 = (3 * c->L + 63) / 64;
 	memset(&c->esz, 0, sizeof c->esz);
-	CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-	CK(cudaEventCreate(&c->ev0));
-	CK(cudaEventCreate(&c->ev1));
-	if (c->alloc(&c->counters, 8) || c->alloc(&c->gpos, 1)) return -1;
-	CK(cudaMemsetAsync(c->counters, 0, 64, c->st));
+	// a context that cannot be completed is taken down again (stream, events, blocks), not leaked
+	auto fail = [&](cudaError_t e, const char *what) {
+		if (e != cudaSuccess) harcgpu_set_error("harcgpu_create: %s: %s", what, cudaGetErrorString(e));
+		harcgpu_destroy(c);
+		return -1;
+	};
+	cudaError_t e;
+	if ((e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) != cudaSuccess) { c->st = nullptr; return fail(e, "cudaStreamCreate"); }
+	if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) { c->ev0 = nullptr; return fail(e, "cudaEventCreate"); }
+	if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) { c->ev1 = nullptr; return fail(e, "cudaEventCreate"); }
+	if (c->alloc(&c->counters, 8) || c->alloc(&c->gpos, 1)) return fail(cudaSuccess, "alloc");
+	if ((e = cudaMemsetAsync(c->counters, 0, 64, c->st)) != cudaSuccess) return fail(e, "cudaMemsetAsync");
 	*out = c;
 	return 0;
 }
@@ -90,16 +97,16 @@ void harcgpu_destroy(harcgpu_ctx *c)
 {
 	if (!c) return;
 	cudaSetDevice(c->device);
-	cudaStreamSynchronize(c->st);
+	if (c->st) cudaStreamSynchronize(c->st);
 	job_close(c);
 	if (c->st_bcast) { cudaStreamSynchronize(c->st_bcast); cudaStreamDestroy(c->st_bcast); cudaEventDestroy(c->ev_packed); cudaEventDestroy(c->ev_bcast); }
 	if (c->st_copy) { cudaStreamSynchronize(c->st_copy); cudaStreamDestroy(c->st_copy); cudaEventDestroy(c->ev_staged); cudaEventDestroy(c->ev_order); }
 	for (auto &b : c->live) cudaFree(b.p);
 	c->trim();
-	cudaEventDestroy(c->ev0);
-	cudaEventDestroy(c->ev1);
+	if (c->ev0) cudaEventDestroy(c->ev0);
+	if (c->ev1) cudaEventDestroy(c->ev1);
 	if (c->evl0) { cudaEventDestroy(c->evl0); cudaEventDestroy(c->evl1); }
-	cudaStreamDestroy(c->st);
+	if (c->st) cudaStreamDestroy(c->st);
 	delete c;
 }
 

@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter_kernel(const u64 *__
 		if (lane == leader && valid) { old = s.wh[w][d]; s.wh[w][d] = old + __popc(peers[i]); }
 		old = __shfl_sync(0xffffffffu, old, leader);
 		rank[i] = old + __popc(peers[i] & lt);
+		__syncwarp(); // the leader of the next item may be another lane that reads the counter this one has just written
 	}
 	__syncthreads();
 	// digit tid (the first 256 threads): starts of the warps' runs inside the digit's run, look-back, then the start of
