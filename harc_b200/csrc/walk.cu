@@ -425,6 +425,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 		// walker the stripe is the whole array and the choice is exactly the reference's.
 		if (state == S_RESTART) {
 			bool got_head = false;
+			__syncwarp(gmask); // the leader's stores of the last restart are ordered before these loads (racecheck)
 			u32 stripe = s.stripe, tried = s.stripes_tried;
 			long long cursor = s.cursor;
 			while (tried < a.walkers) {

@@ -17,3 +17,6 @@ except Exception as e:
     print("$f", "ERR", e); print(open("$O/s13_$f.err").read()[-1500:])
 P
 done
+# racecheck again after the __syncwarp in the sort's ranking loop (one golden fixture is enough to run every sort route)
+timeout 900 /usr/local/cuda/bin/compute-sanitizer --tool racecheck --print-limit 5 --log-file $O/sanitizer_racecheck2.log python -m pytest tests/test_golden_gpu.py -m gpu -x -q -k "L100_RC or repeats" > $O/sanitizer_racecheck2_pytest.log 2>&1
+tail -2 $O/sanitizer_racecheck2_pytest.log; grep -E "RACECHECK SUMMARY" $O/sanitizer_racecheck2.log
