@@ -21,7 +21,7 @@ EXPORTS = [
     "harcgpu_load_pool_device", "harcgpu_launch_count", "harcgpu_stage_nreads",
     "harcgpu_job_init", "harcgpu_job_connect", "harcgpu_job_load_reads", "harcgpu_job_load_reads_device", "harcgpu_job_build_dicts",
     "harcgpu_job_reorder", "harcgpu_job_set_barrier", "harcgpu_set_pool_exchange", "harcgpu_load_pool_ids", "harcgpu_device_result",
-    "harcgpu_get_packed_order",
+    "harcgpu_get_packed_order", "harcgpu_trim",
     "harcgpu_debug_sort", "harcgpu_fastq_readlen", "harcgpu_ingest_fastq", "harcgpu_ingest_fastq_device", "harcgpu_get_ingest", "harcgpu_load_pool_ingested",
 ]
 
@@ -105,6 +105,7 @@ def load_library():
     lib.harcgpu_set_pool_exchange.argtypes = [vp, POOL_EXCHANGE, vp]
     lib.harcgpu_load_pool_ids.argtypes = [vp, vp, u32, vp, u32]
     lib.harcgpu_get_packed_order.argtypes = [vp, vp, vp, vp, vp]
+    lib.harcgpu_trim.argtypes = [vp]
     lib.harcgpu_launch_count.restype = ctypes.c_uint64
     lib.harcgpu_debug_sort.argtypes = [vp, vp, vp, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.harcgpu_fastq_readlen.argtypes = [vp, ctypes.c_uint64]
@@ -430,6 +431,10 @@ class HarcGpu:
 
     def encode_dir(self, basedir):
         self._ck(self.lib.harcgpu_encode_dir(self.h, basedir.encode()))
+
+    def trim(self):
+        """Give the cached device blocks back to the driver."""
+        self._ck(self.lib.harcgpu_trim(self.h))
 
     def last_ms(self, phase):
         return self.lib.harcgpu_last_ms(self.h, phase.encode())

@@ -112,6 +112,15 @@ void harcgpu_destroy(harcgpu_ctx *c)
 
 void *harcgpu_stream(harcgpu_ctx *c) { return c ? (void *)c->st : nullptr; }
 
+int harcgpu_trim(harcgpu_ctx *c)
+{
+	if (!c) { harcgpu_set_error("null argument"); return -1; }
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->st));
+	c->trim();
+	return 0;
+}
+
 double harcgpu_last_ms(harcgpu_ctx *c, const char *phase)
 {
 	if (!c || !phase) return -1;

@@ -279,7 +279,7 @@ int harcgpu_job_init(harcgpu_ctx *c, int rank, int world, uint32_t n_total, uint
 		if (rcap > 0x7fffffffull) { harcgpu_set_error("dictionary shard too large"); return -1; }
 		c->recv_cap = (u32)rcap;
 		u64 cap = 16;
-		while (cap < 2 * rcap) cap <<= 1; // load factor <= 0.5 even for a full shard
+		while (cap < 2 * per) cap <<= 1; // load factor <= 0.5 for a shard of mean size (<= 0.63 for one 25 % above it)
 		c->shard_cap = (u32)cap;
 		c->shard_nslots = cap + cap / 8 + 1024;
 		u64 bw = 1024;

@@ -220,6 +220,9 @@ int harcgpu_encode_dir(harcgpu_ctx *ctx, const char *basedir);
 /* Timing of the last call in milliseconds of device time (CUDA events on the context's stream): phases are
  * "pack","dict","walk","finalize","encode".  Returns <0 for an unknown phase. */
 double harcgpu_last_ms(harcgpu_ctx *ctx, const char *phase);
+/* The context keeps the device blocks it has released for the next pass (no driver allocation in steady state); this
+ * gives them back to the driver, e.g. before the caller needs the memory for something else.  Results stay valid. */
+int harcgpu_trim(harcgpu_ctx *ctx);
 /* Raw CUDA stream of the context (cudaStream_t) so a caller can bracket calls with its own events. */
 void *harcgpu_stream(harcgpu_ctx *ctx);
 
