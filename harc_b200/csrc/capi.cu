@@ -99,7 +99,10 @@ void harcgpu_destroy(harcgpu_ctx *c)
 	cudaSetDevice(c->device);
 	if (c->st) cudaStreamSynchronize(c->st);
 	job_close(c);
-	if (c->st_bcast) { cudaStreamSynchronize(c->st_bcast); cudaStreamDestroy(c->st_bcast); cudaEventDestroy(c->ev_packed); cudaEventDestroy(c->ev_bcast); }
+	if (c->st_bcast) {
+		cudaStreamSynchronize(c->st_bcast); cudaStreamDestroy(c->st_bcast); cudaEventDestroy(c->ev_packed); cudaEventDestroy(c->ev_bcast);
+		for (int r = 0; r < 8; r++) { cudaStreamSynchronize(c->st_peer[r]); cudaStreamDestroy(c->st_peer[r]); cudaEventDestroy(c->ev_peer[r]); }
+	}
 	if (c->st_copy) { cudaStreamSynchronize(c->st_copy); cudaStreamDestroy(c->st_copy); cudaEventDestroy(c->ev_staged); cudaEventDestroy(c->ev_order); }
 	for (auto &b : c->live) cudaFree(b.p);
 	c->trim();

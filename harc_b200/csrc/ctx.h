@@ -62,7 +62,9 @@ struct harcgpu_ctx {
 	bool shard_ready = false, job_reads_loaded = false;
 	cudaStream_t st_bcast = nullptr;      // side stream of the broadcast of this GPU's packed slice
 	cudaEvent_t ev_packed = nullptr, ev_bcast = nullptr;
-	bool bcast_pending = false, bcast_needed = false;
+	bool bcast_pending = false, bcast_needed = false, bcast_dma = false;
+	cudaStream_t st_peer[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // one copy stream per peer
+	cudaEvent_t ev_peer[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	int (*pool_exchange)(void *user, void *d_best, uint64_t count) = nullptr;
 	void *pool_exchange_user = nullptr;
 	int (*job_barrier_hook)(void *user) = nullptr; // ranks that share one GPU (tests): host barrier instead of the barrier kernel

@@ -162,7 +162,10 @@ int job_bloom_insert(harcgpu_ctx *c, const u64 *mixed_keys, u32 nk, int l, int w
 
 void job_close(harcgpu_ctx *c)
 {
-	if (c->st_bcast) cudaStreamSynchronize(c->st_bcast);
+	if (c->st_bcast) {
+		cudaStreamSynchronize(c->st_bcast);
+		for (int r = 0; r < 8; r++) cudaStreamSynchronize(c->st_peer[r]);
+	}
 	c->bcast_pending = false;
 	if (c->arena[c->shard_rank]) { c->reads = nullptr; c->n = 0; c->dicts_built = false; c->reordered = false; } // the reads lived in the arena
 	for (int r = 0; r < 8; r++) {
@@ -195,33 +198,52 @@ int job_barrier(harcgpu_ctx *c)
 	return 0;
 }
 
-// starts the broadcast of this GPU's packed slice on the side stream (behind everything queued on the compute stream so far)
+// Starts the broadcast of this GPU's packed slice (behind everything queued on the compute stream so far).  Two routes:
+// job_bcast_kernel (default: plain stores into the peers' replicas), or the copy engines (HARCGPU_JOB_BCAST=dma: one
+// cudaMemcpyAsync per peer, each on a stream of its own).  Measured on 8 GPUs: the kernel route 61.7 ms per step at
+// configs[2] and 255.8 ms at configs[4], the copy engines 71.2 and 310.2 ms -- seven peer copies per GPU do not reach the
+// NVLink egress that 74 blocks of storing threads do, and the walk ends up waiting for them.  Neither hides completely:
+// the same per-GPU dictionary work takes 45 ms next to a 4 GB broadcast (N = 2) and 84 ms next to a 28 GB one (N = 8).
 static int job_bcast_start(harcgpu_ctx *c)
 {
 	if (!c->bcast_needed) return 0;
 	c->bcast_needed = false;
 	const u32 n_local = c->job_nloc;
 	u64 *mine = (u64 *)(c->arena[c->shard_rank] + c->arena_reads_off) + (size_t)c->job_base * c->NW;
-	{
-		if (!c->st_bcast) {
-			CK(cudaStreamCreateWithFlags(&c->st_bcast, cudaStreamNonBlocking));
-			CK(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
-			CK(cudaEventCreateWithFlags(&c->ev_bcast, cudaEventDisableTiming));
+	if (!c->st_bcast) {
+		CK(cudaStreamCreateWithFlags(&c->st_bcast, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&c->ev_bcast, cudaEventDisableTiming));
+		for (int r = 0; r < 8; r++) {
+			CK(cudaStreamCreateWithFlags(&c->st_peer[r], cudaStreamNonBlocking));
+			CK(cudaEventCreateWithFlags(&c->ev_peer[r], cudaEventDisableTiming));
 		}
-		CK(cudaEventRecord(c->ev_packed, c->st));
+		const char *e = getenv("HARCGPU_JOB_BCAST");
+		c->bcast_dma = e && !strcmp(e, "dma");
+	}
+	CK(cudaEventRecord(c->ev_packed, c->st));
+	const size_t words = (size_t)n_local * c->NW;
+	if (c->bcast_dma) {
+		for (int r = 0; r < c->shard_world; r++) {
+			if (r == c->shard_rank) continue;
+			void *dst = (void *)((u64 *)(c->arena[r] + c->arena_reads_off) + (size_t)c->job_base * c->NW);
+			CK(cudaStreamWaitEvent(c->st_peer[r], c->ev_packed, 0));
+			CK(cudaMemcpyAsync(dst, mine, words * 8, cudaMemcpyDefault, c->st_peer[r]));
+			CK(cudaEventRecord(c->ev_peer[r], c->st_peer[r]));
+		}
+	} else {
 		CK(cudaStreamWaitEvent(c->st_bcast, c->ev_packed, 0));
 		BcastDst dst;
 		for (int r = 0; r < 8; r++)
 			dst.p[r] = r < c->shard_world ? (void *)((u64 *)(c->arena[r] + c->arena_reads_off) + (size_t)c->job_base * c->NW) : nullptr;
-		const size_t words = (size_t)n_local * c->NW;
 		if (((uintptr_t)mine & 15) == 0 && words % 2 == 0)
 			job_bcast_kernel<uint4><<<KL + 74, 512, 0, c->st_bcast>>>((const uint4 *)mine, words / 2, dst, c->shard_world, c->shard_rank);
 		else
 			job_bcast_kernel<u64><<<KL + 74, 512, 0, c->st_bcast>>>((const u64 *)mine, words, dst, c->shard_world, c->shard_rank);
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(c->ev_bcast, c->st_bcast));
-		c->bcast_pending = true;
 	}
+	c->bcast_pending = true;
 	return 0;
 }
 
@@ -230,7 +252,10 @@ static int job_bcast_join(harcgpu_ctx *c)
 {
 	if (job_bcast_start(c)) return -1; // (not started yet: a caller that skipped the dictionary build)
 	if (c->bcast_pending) {
-		CK(cudaStreamWaitEvent(c->st, c->ev_bcast, 0));
+		if (c->bcast_dma) {
+			for (int r = 0; r < c->shard_world; r++)
+				if (r != c->shard_rank) CK(cudaStreamWaitEvent(c->st, c->ev_peer[r], 0));
+		} else CK(cudaStreamWaitEvent(c->st, c->ev_bcast, 0));
 		c->bcast_pending = false;
 	}
 	return 0;
