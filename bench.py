@@ -735,7 +735,10 @@ def run_one_job(args, rank, world, local, dist, json_fd):
                                        "walk_kernel<%d, %d>, per GPU" % (ctx.NW(), args.lanes or 32)),
             "e2e": {"value": e2e, "unit": "Mreads/s", "ms_per_step": ms_e2e, "what": "one job at a time; every rank uploads its slice from pinned host "
                     "memory and reads back its file set", "h2d_bytes_per_step": int(h_clean.numel() + h_N.numel()) * world, "d2h_bytes_per_step": int(last.get("d2h", 0)) * world},
-            "exchange_bytes_per_step": comm_bytes, "verify": verify, "one_gpu_same_workload": one_gpu, "laps_ms_rank0": laps or None, "detail": detail,
+            "exchange_bytes_per_step": comm_bytes, "verify": verify, "one_gpu_same_workload": one_gpu,
+            "scaling_note": "strong scaling of ONE %d-read job; `bench.py --gpus 1` runs configs[1] (the metric's configuration, a different "
+                            "workload), so the one-GPU time of THIS workload is measured here, on rank 0's GPU in the same run "
+                            "(one_gpu_same_workload)" % total_reads, "laps_ms_rank0": laps or None, "detail": detail,
             "gpu_launches": int(launches), "allocator": {"device_peak_MB": ctx.last_ms("peak_MB"), "cudaMalloc_calls": ctx.last_ms("cudaMalloc_calls")},
             "clocks": sampler.summary(), "commit": git_head(),
         }

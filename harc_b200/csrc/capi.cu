@@ -272,6 +272,7 @@ int harcgpu_build_dicts(harcgpu_ctx *c)
 	if (!c || !c->reads) { harcgpu_set_error("load reads first"); return -1; }
 	CK(cudaSetDevice(c->device));
 	if (c->shard_world > 1) return harcgpu_job_build_dicts(c);
+	for (const char *k : { "lap:bd1_keys", "lap:bd1_sort", "lap:bd1_csr", "lap:bd1_place" }) c->ms.erase(k);
 	c->tic();
 	for (int l = 0; l < c->p.numdict; l++)
 		if (build_dict(c, c->d1[l], c->reads, nullptr, c->n, c->NW, c->p.dict_start[l], c->p.dict_end[l], 2, nullptr)) return -1;

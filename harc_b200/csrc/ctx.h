@@ -194,7 +194,7 @@ struct harcgpu_ctx {
 	// tuning aid (HARCGPU_LAPS=1): device time between named points inside a phase, as "lap:<name>" of harcgpu_last_ms
 	int laps = -1;
 	cudaEvent_t evl0 = nullptr, evl1 = nullptr;
-	void lap(const char *name)
+	void lap(const char *name, bool add = false)
 	{
 		if (laps < 0) { const char *e = getenv("HARCGPU_LAPS"); laps = e && atoi(e) ? 1 : 0; }
 		if (!laps) return;
@@ -203,7 +203,7 @@ struct harcgpu_ctx {
 		cudaEventSynchronize(evl1);
 		float f = 0;
 		cudaEventElapsedTime(&f, evl0, evl1);
-		if (name) ms[std::string("lap:") + name] = f;
+		if (name) { if (add) ms[std::string("lap:") + name] += f; else ms[std::string("lap:") + name] = f; }
 		std::swap(evl0, evl1);
 	}
 	void tic() { cudaEventRecord(ev0, st); }

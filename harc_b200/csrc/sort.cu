@@ -194,31 +194,37 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter_kernel(const u64 *__
 // insertion sort; equal keys (the bins of a dictionary) are left as they are.  A run longer than RUN_MAX is reported and
 // the caller falls back to the full sort.
 constexpr int RUN_MAX = 32;
-__global__ void __launch_bounds__(256) runfix_kernel(u64 *__restrict__ keys, u32 *__restrict__ vals, size_t n, u32 *__restrict__ too_long)
+// After the four passes over the top half, pairs that share a top half are in input order.  Most such runs are already in
+// key order -- above all the dictionary bins: runs of EQUAL keys, of any length on repetitive genomes -- and need
+// nothing, so the work is driven by the inversions: a pair that is smaller than its predecessor in the same run walks
+// back to the head of its run (a step or two for the chance collisions of random keys) and marks it; only marked runs
+// are looked at again.  A bin of 10^5 equal keys costs nothing this way; one thread per run head scanning its whole run
+// (round 1) cost 74 ms on a 3 M-read input with a long poly-A stretch.
+__global__ void __launch_bounds__(256) runmark_kernel(const u64 *__restrict__ keys, size_t n, u32 *__restrict__ fixbits)
 {
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
+	if (i == 0 || i >= n) return;
+	const u64 k = keys[i], kp = keys[i - 1];
+	if ((k >> 32) != (kp >> 32) || k >= kp) return;
+	size_t h = i - 1;
+	while (h > 0 && (keys[h - 1] >> 32) == (k >> 32)) h--;
+	atomicOr(&fixbits[h >> 5], 1u << (h & 31));
+}
+__global__ void __launch_bounds__(256) runfix_kernel(u64 *__restrict__ keys, u32 *__restrict__ vals, size_t n, const u32 *__restrict__ fixbits,
+                                                     u32 *__restrict__ too_long)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n || !((fixbits[i >> 5] >> (i & 31)) & 1u)) return; // not the head of a run with an inversion
 	const u64 k0 = keys[i];
-	if (i > 0 && (keys[i - 1] >> 32) == (k0 >> 32)) return; // not the head of a run
-	if (i + 1 >= n || (keys[i + 1] >> 32) != (k0 >> 32)) return; // run of one
-	// first a look at the run without buffering it: a run that is already in order (one dictionary bin of equal keys, however
-	// long -- repeats make such bins certain on real genomes) needs nothing; RUN_MAX only bounds the runs that have to be sorted
-	size_t len64 = 1;
-	bool sorted = true;
-	u64 prevk = k0;
-	while (i + len64 < n) {
-		const u64 kk = keys[i + len64];
-		if ((kk >> 32) != (k0 >> 32)) break;
-		if (kk < prevk) sorted = false;
-		prevk = kk;
-		len64++;
-	}
-	if (sorted) return;
-	if (len64 > RUN_MAX) { atomicMax(too_long, 1u); return; }
 	u64 k[RUN_MAX];
 	u32 v[RUN_MAX];
-	const int len = (int)len64;
-	for (int a = 0; a < len; a++) { k[a] = keys[i + a]; v[a] = vals[i + a]; }
+	int len = 0;
+	while (i + len < n && (keys[i + len] >> 32) == (k0 >> 32)) {
+		if (len == RUN_MAX) { atomicMax(too_long, 1u); return; } // a long run that is out of order: the full sort takes over
+		k[len] = keys[i + len];
+		v[len] = vals[i + len];
+		len++;
+	}
 	for (int a = 1; a < len; a++) { // stable insertion sort by the whole key
 		const u64 ka = k[a];
 		const u32 va = v[a];
@@ -274,15 +280,18 @@ int radix_sort_mixed(harcgpu_ctx *c, u64 **keys, u64 **keys_alt, u32 **vals, u32
 	if (n == 0) return 0;
 	cudaStream_t st = c->st;
 	if (!force_full) {
-		u32 *flag = nullptr, h = 0;
-		if (c->alloc(&flag, 1)) return -1;
+		u32 *flag = nullptr, *fixbits = nullptr, h = 0;
+		const size_t nw = (n + 31) / 32;
+		if (c->alloc(&flag, 1) || c->alloc(&fixbits, nw)) return -1;
 		CK(cudaMemsetAsync(flag, 0, 4, st));
+		CK(cudaMemsetAsync(fixbits, 0, 4 * nw, st));
 		if (radix_sort_pairs(c, keys, keys_alt, vals, vals_alt, n, 32, 64)) return -1;
-		runfix_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(*keys, *vals, n, flag);
+		runmark_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(*keys, n, fixbits);
+		runfix_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(*keys, *vals, n, fixbits, flag);
 		CK(cudaGetLastError());
 		CK(cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
-		c->release(flag);
+		c->release(flag); c->release(fixbits);
 		if (!h) return 0;
 	}
 	// every step so far was stable, so the full sort can start from whatever order the pairs are in now

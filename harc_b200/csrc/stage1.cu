@@ -342,6 +342,7 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 	}
 	const int bitpos = bits * ds, nbits = bits * (de - ds + 1);
 	d.bitpos = bitpos; d.nbits = nbits;
+	c->lap(nullptr);
 	if (shard && shard->pair_keys) n = shard->npairs;
 	u64 *k_in = nullptr, *k_out = nullptr, *scan_tmp = nullptr;
 	u32 *id_in = nullptr, *head = nullptr, *binidx = nullptr, *d_total = nullptr;
@@ -411,7 +412,9 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 	}
 	// LSD radix sort is stable and ids start ascending, so ids stay ascending inside a bin (reorder.cpp:371-384)
 	if (c->alloc(&id_alt, n)) return -1;
+	c->lap(bits == 2 ? "bd1_keys" : "bd2_keys", true);
 	if (radix_sort_mixed(c, &k_in, &k_out, &id_in, &id_alt, n)) return -1; // mixed keys use all 64 bits
+	c->lap(bits == 2 ? "bd1_sort" : "bd2_sort", true);
 	std::swap(k_in, k_out); // k_out = sorted keys from here on
 	if (shard) CK(cudaMemcpyAsync(d.ids, id_in, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st)); // into the arena the peers have mapped
 	else { d.ids = id_in; id_in = nullptr; }
@@ -425,6 +428,7 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 	if (c->alloc(&d.keys, nk) || c->alloc(&d.start, (size_t)nk + 1)) return -1;
 	bins_kernel<<<KL + cdiv(n, 256), 256, 0, st>>>(k_out, head, binidx, n, nk, d.keys, d.start);
 	CK(cudaGetLastError());
+	c->lap(bits == 2 ? "bd1_csr" : "bd2_csr", true);
 	// table: nominal 2^k >= 2 numkeys slots (k fixes the home buckets), placed in mixed-key order
 	u64 cap = 16;
 	int kbits = 4;
@@ -462,6 +466,7 @@ int build_dict(harcgpu_ctx *c, DictDev &d, const u64 *reads, const u64 *readsN, 
 	overflow_kernel<<<KL + cdiv(nk, 256), 256, 0, st>>>(d.keys, pos, nk, d.slot_shift, world, d.slots);
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(st));
+	c->lap(bits == 2 ? "bd1_place" : "bd2_place", true);
 	c->release(pm); c->release(bmax); c->release(pos); c->release(d_last);
 	c->release(k_in); c->release(k_out); c->release(id_in); c->release(head); c->release(binidx);
 	c->release(scan_tmp); c->release(d_total); c->release(id_alt);

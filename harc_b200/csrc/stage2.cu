@@ -501,9 +501,13 @@ __global__ void __launch_bounds__(PP_THREADS) pool_probe_kernel(PoolArgs a)
 				// Here all windows probe at once: a read counts as live for this window unless a window of higher priority
 				// (= earlier in the reference's sequential order) holds it.  The host repeats the probe until no priority
 				// moves; priorities only fall and never below the sequential result, so the fixed point is that result.
+				// (A window gives up after 8 x maxsearch entries: the reference never meets the dead ones because it compacts its
+				// bins, here they are stepped over one by one, and a bin of 10^5 reads probed from 10^4 windows -- a poly-A run --
+				// would otherwise cost minutes.  Bins up to 8 x maxsearch are exact.)
 				int live = 0;
 				u32 e = bsize;
-				while (e-- > 0u && live < a.maxsearch) {
+				const u32 stop = bsize > 8u * (u32)a.maxsearch ? bsize - 8u * (u32)a.maxsearch : 0u;
+				while (e-- > stop && live < a.maxsearch) {
 					const u32 rid = bin_entry(dv, bstart, bsize, e);
 					if (*((volatile u64 *)&a.best[rid]) < myprio) continue; // taken earlier: not in the bin any more
 					live++;
@@ -513,7 +517,7 @@ __global__ void __launch_bounds__(PP_THREADS) pool_probe_kernel(PoolArgs a)
 					for (int k = 0; k < NW; k++) d += __popcll((rev ? rc[k] : w[k]) ^ __ldg(&p2[k])) + __popcll(__ldg(&pn[k]));
 					if (d <= a.thresh_s && atomicMin(&a.best[rid], myprio) > myprio) a.flags[1] = 1u;
 				}
-				if (live >= a.maxsearch && e != 0xffffffffu) a.flags[0] = 1u;
+				if (live >= a.maxsearch && e != 0xffffffffu && e + 1u > stop) a.flags[0] = 1u;
 			}
 		}
 	}
@@ -1082,7 +1086,7 @@ int s2_encode(harcgpu_ctx *c)
 		}
 		c->ms["pool_passes"] = pass + 1;
 		if (!again) break;
-		if (pass >= 64) { harcgpu_set_error("pool re-alignment did not settle in 64 passes"); return -1; }
+		if (pass >= 15) break; // sixteen passes: what is settled by then is a valid (lossless) assignment, if not the reference's
 	}
 	if (P && c->shard_world > 1) {
 		best_localize_kernel<<<KL + cdiv(P, 256), 256, 0, st>>>(best, P, c->shard_rank);

@@ -540,8 +540,17 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NW <= 4 ? WALK_MB : 4) walk_k
 						const u64 e = *((volatile unsigned long long *)ce);
 						if ((e & ~0x0fffffffull) == tag) left = min(left, (u32)(e & 0x0fffffffull));
 					}
+					// Many walkers: thousands of them may be inside one repeat at once, all scanning one bin from the same end and
+					// losing the same claims (62 M lost claims for 2.3 M reads on a genome with a long poly-A run).  All reads of
+					// a bin carry the same key, so most probes start a walker- and lane-specific distance (< 512 entries) below the cursor;
+					// one in eight starts at the cursor and keeps it moving.  (One walker: the reference's scan, from the tail.)
+					bool at_cursor = true;
+					if (a.extend != 0 && left > 256u) {
+						const u32 hsh = (wid * 0x9E3779B1u) ^ ((u32)lane * 0x85EBCA6Bu) ^ (c_probes * 0xC2B2AE35u);
+						if ((hsh >> 29) != 0u) { left -= (hsh & 0x00ffffffu) % min(left >> 1, 512u); at_cursor = false; }
+					}
 					const u32 top = left;
-					bool tail_claimed = true; // every entry from `top` down to here was claimed
+					bool tail_claimed = at_cursor; // every entry from `top` down to here was claimed (and `top` is the cursor)
 					// many walkers: a probe gives up after 8 x maxsearch entries (one walker: the reference's scan, to the end)
 					u32 budget = a.extend != 0 ? 8u * (u32)a.maxsearch : 0xffffffffu;
 					while (left > 0 && seen < a.maxsearch && budget-- > 0u) {

@@ -69,14 +69,17 @@ def test_long_bins_of_equal_keys_stay_on_the_fast_path():
     rng = np.random.default_rng(12)
     base = rng.integers(0, 2 ** 64, size=100000, dtype=np.uint64)
     bins = [np.full(n, k, dtype=np.uint64) for n, k in ((33, 0xAAAA000011112222), (1000, 0x0123456789ABCDEF), (50000, 0))]
-    # and a run of two different keys with one top half, of which one is a long bin
-    mixed = np.concatenate([np.full(400, 0xBEEF000000000007, dtype=np.uint64), np.full(3, 0xBEEF000000000003, dtype=np.uint64)])
-    keys = np.concatenate([base] + bins + [mixed])
+    keys = np.concatenate([base] + bins)
     rng.shuffle(keys)
     l0 = harc_b200.launch_count()
     _check(ctx, keys, 1)
     fast = harc_b200.launch_count() - l0
     l0 = harc_b200.launch_count()
     _check(ctx, keys[: len(base)], 1)
-    assert fast - (harc_b200.launch_count() - l0) < 8, "long bins of equal keys must not trigger the eight-pass fallback"
+    assert fast == harc_b200.launch_count() - l0, "long bins of equal keys must not trigger the eight-pass fallback"
+    # a long bin that shares its top half with a few smaller keys is out of order after the four passes: the fallback sorts it
+    mixed = np.concatenate([np.full(400, 0xBEEF000000000007, dtype=np.uint64), np.full(3, 0xBEEF000000000003, dtype=np.uint64)])
+    keys = np.concatenate([base, mixed])
+    rng.shuffle(keys)
+    _check(ctx, keys, 1)
     ctx.close()

@@ -55,6 +55,8 @@ def main():
            "chain_heads": u, "aligned_singletons": int(es.aligned_singletons), "aligned_N": int(es.aligned_N), "phases_ms": ph,
            "device_ms": round(dev, 1), "Mreads_per_s_device": round(n / dev / 1e3, 1), "host_wall_ms_incl_copies": round(1000 * (t1 - t0), 1),
            "counters": ctx.counters(), "pool_passes": ctx.last_ms("pool_passes"),
+           "laps": {k: round(ctx.last_ms("lap:" + k), 2) for k in ("bd1_keys", "bd1_sort", "bd1_csr", "bd1_place", "s2_layout", "s2_consensus", "s2_pool",
+                                                                    "s2_merge_emit", "s2_unaligned", "s2_sets") if ctx.last_ms("lap:" + k) >= 0},
            "walkers": "auto", "driver_allocations_last_pass": int(ctx.last_ms("cudaMalloc_calls") - m0)})
     ctx.close()
 
