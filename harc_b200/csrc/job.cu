@@ -279,6 +279,7 @@ int harcgpu_job_init(harcgpu_ctx *c, int rank, int world, uint32_t n_total, uint
 {
 	if (!c || world < 1 || world > 8 || rank < 0 || rank >= world) { harcgpu_set_error("bad job arguments (1..8 GPUs)"); return -1; }
 	if ((u64)base + n_local > n_total) { harcgpu_set_error("slice [%u, %u + %u) exceeds the %u reads of the job", base, base, n_local, n_total); return -1; }
+	if (c->p.shard_dicts != 0 && world > 1 && (world & (world - 1))) { harcgpu_set_error("sharded dictionaries need 2, 4 or 8 GPUs"); return -1; }
 	CK(cudaSetDevice(c->device));
 	CK(cudaStreamSynchronize(c->st));
 	job_close(c);
@@ -291,7 +292,6 @@ int harcgpu_job_init(harcgpu_ctx *c, int rank, int world, uint32_t n_total, uint
 	c->seg_per = (uint32_t)((((uint64_t)n_total + world - 1) / world + 31) / 32 * 32);
 	if (c->seg_per == 0) c->seg_per = 32;
 	c->dicts_sharded = c->p.shard_dicts != 0 && world > 1;
-	if (c->dicts_sharded && (world & (world - 1))) { harcgpu_set_error("sharded dictionaries need 2, 4 or 8 GPUs"); return -1; }
 	c->job_bloom = 1;
 	if (const char *e = getenv("HARCGPU_JOB_BLOOM")) c->job_bloom = atoi(e);
 	// arena layout (the same on every rank)
