@@ -352,6 +352,8 @@ struct PoolArgs {
 	int L, thresh_s, maxsearch;
 	u64 *best;
 	u32 *flags;    // [0]: a scan of a bin beyond maxsearch ended with entries left; [1]: such a scan lowered a priority in this pass
+	unsigned long long *pcur; // cursor cache of the bins beyond 8 x maxsearch
+	u32 pcur_mask;
 	u64 rank_bits; // rank << RANK_SHIFT
 	const u32 *bloom; u32 bloom_mask;
 	const u32 *T; // tile index
@@ -504,12 +506,29 @@ __global__ void __launch_bounds__(PP_THREADS) pool_probe_kernel(PoolArgs a)
 				// (A window gives up after 8 x maxsearch entries: the reference never meets the dead ones because it compacts its
 				// bins, here they are stepped over one by one, and a bin of 10^5 reads probed from 10^4 windows -- a poly-A run --
 				// would otherwise cost minutes.  Bins up to 8 x maxsearch are exact.)
+				// Bins beyond 8 x maxsearch (where the result is approximate anyway) also keep a cursor in a small direct-mapped
+				// cache: an index above which every read has been taken by SOME window, so the scan starts below the part of the
+				// bin that is used up instead of stepping over it read by read, window after window and pass after pass.
 				int live = 0;
 				u32 e = bsize;
-				const u32 stop = bsize > 8u * (u32)a.maxsearch ? bsize - 8u * (u32)a.maxsearch : 0u;
+				const bool huge = bsize > 8u * (u32)a.maxsearch && bsize < (1u << 28);
+				const u64 ctag = ((u64)bstart << 32) | ((u64)l << 31);
+				unsigned long long *ce = a.pcur + ((bstart * 2u + (u32)l) & a.pcur_mask);
+				if (huge) {
+					const u64 cv = *((volatile unsigned long long *)ce);
+					if ((cv & ~0x0fffffffull) == ctag) e = min(e, (u32)(cv & 0x0fffffffull));
+				}
+				const u32 top = e;
+				bool used_up = huge; // every read from `top` down to here is taken
+				const u32 stop = e > 8u * (u32)a.maxsearch ? e - 8u * (u32)a.maxsearch : 0u;
 				while (e-- > stop && live < a.maxsearch) {
 					const u32 rid = bin_entry(dv, bstart, bsize, e);
-					if (*((volatile u64 *)&a.best[rid]) < myprio) continue; // taken earlier: not in the bin any more
+					const u64 owner = *((volatile u64 *)&a.best[rid]);
+					if (used_up && owner == NOBEST) {
+						used_up = false;
+						if (e + 1u < top) *((volatile unsigned long long *)ce) = ctag | (u64)(e + 1u);
+					}
+					if (owner < myprio) continue; // taken earlier: not in the bin any more
 					live++;
 					const u64 *p2 = a.pool + (size_t)rid * NW, *pn = a.poolN + (size_t)rid * NW;
 					int d = 0;
@@ -517,6 +536,7 @@ __global__ void __launch_bounds__(PP_THREADS) pool_probe_kernel(PoolArgs a)
 					for (int k = 0; k < NW; k++) d += __popcll((rev ? rc[k] : w[k]) ^ __ldg(&p2[k])) + __popcll(__ldg(&pn[k]));
 					if (d <= a.thresh_s && atomicMin(&a.best[rid], myprio) > myprio) a.flags[1] = 1u;
 				}
+				if (used_up && e + 1u < top && e != 0xffffffffu) *((volatile unsigned long long *)ce) = ctag | (u64)(e + 1u);
 				if (live >= a.maxsearch && e != 0xffffffffu && e + 1u > stop) a.flags[0] = 1u;
 			}
 		}
@@ -1034,9 +1054,12 @@ int s2_encode(harcgpu_ctx *c)
 	u32 *af = nullptr, *exa = nullptr, *rid_u = nullptr, *irid = nullptr;
 	u32 M = 0, M_single = 0;
 	u32 *pflags = nullptr;
+	unsigned long long *pcur = nullptr;
+	constexpr u32 PCUR_ENTRIES = 1u << 16;
 	PoolArgs pa;
 	bool have_probe = false;
-	if (c->alloc(&best, (size_t)P + 1) || c->alloc(&pflags, 2)) return -1;
+	if (c->alloc(&best, (size_t)P + 1) || c->alloc(&pflags, 2) || c->alloc(&pcur, PCUR_ENTRIES)) return -1;
+	CK(cudaMemsetAsync(pcur, 0xff, 8 * (size_t)PCUR_ENTRIES, st)); // no bin has this tag
 	if (P) {
 		fill64_kernel<<<KL + cdiv(P, 256), 256, 0, st>>>(best, P, NOBEST);
 		CK(cudaGetLastError());
@@ -1050,7 +1073,7 @@ int s2_encode(harcgpu_ctx *c)
 			a.d[l].dstart = c->d2[l].bitpos / 3; a.d[l].dend = a.d[l].dstart + c->d2[l].nbits / 3 - 1;
 			a.d[l].world = 0;
 		}
-		a.L = L; a.thresh_s = c->p.thresh_s; a.maxsearch = c->p.maxsearch; a.best = best; a.flags = pflags;
+		a.L = L; a.thresh_s = c->p.thresh_s; a.maxsearch = c->p.maxsearch; a.best = best; a.flags = pflags; a.pcur = pcur; a.pcur_mask = PCUR_ENTRIES - 1;
 		a.rank_bits = (u64)(c->shard_world > 1 ? c->shard_rank : 0) << RANK_SHIFT;
 		a.bloom = c->bloom2; a.bloom_mask = c->bloom2_mask; a.T = tile_idx; a.nt = nt_host; a.cwords = cwords + 2;
 		pa = a;
@@ -1256,7 +1279,7 @@ int s2_encode(harcgpu_ctx *c)
 		c->esz.aligned_N = M - M_single;
 	}
 	c->s2_keep.push_back(posb); c->s2_keep.push_back(noise); c->s2_keep.push_back(noisepos);
-	void *tmp[] = { pflags, tile_idx, ns, ex, nat_idx, cs, cid, cstart, inc, G, scan_tmp, d_tot32, d_tot64, cons2, best, prio_u, iprio, af, exa, rid_u, irid,
+	void *tmp[] = { pflags, pcur, tile_idx, ns, ex, nat_idx, cs, cid, cstart, inc, G, scan_tmp, d_tot32, d_tot64, cons2, best, prio_u, iprio, af, exa, rid_u, irid,
 	                f_src, f_kind, f_col, nm1, noff, revc, isN, exN, ordv, uf, exU, ulist, d_tail };
 	for (void *q : tmp) c->release(q);
 	c->encoded = true;
