@@ -4,8 +4,8 @@
 //
 // What crosses NVLink, all of it by kernels of this library over peer memory (no library collective):
 //   * packed reads      -- every GPU packs its slice of the input and job_bcast_kernel stores the packed slice into the
-//                          replica of every other GPU, on a side stream next to the dictionary build (which only needs the
-//                          local slice): the all-gather of the packed reads, hidden behind the build;
+//                          replica of every other GPU, on a side stream next to the shard build (which only needs the
+//                          pairs): the all-gather of the packed reads, mostly hidden behind the build;
 //   * (key, id) pairs   -- every GPU extracts the dictionary keys of its slice, cuts them by owner (one stable radix pass
 //                          over the shard bits) and job_push_kernel stores every range straight into the owner's receive
 //                          buffer at the offset that follows from the 8 x 8 count matrix (every GPU broadcasts its row):

@@ -8,7 +8,12 @@
 // 2 x 2^24 striped locks and its in-place bin compaction); the consensus window of updaterefcount lives in shared
 // memory as a circular array of vote keys.  Everything on the hot path works on 32-bit words (funnel shifts over
 // zero-padded shared-memory arrays, compare masks from a per-block table), because the kernel is bound by instruction
-// issue and dependent latency, not by bandwidth (profiles/).
+// issue and dependent latency, not by bandwidth (profiles/).  A blocked Bloom filter over the keys of both dictionaries,
+// small enough to stay in L2, is asked before the key tables (three of four probes are for keys in no dictionary), and
+// bins of many reads (repeats) are scanned through a cursor cache instead of from their used-up tail.
+//
+// One job on several GPUs (job.cu): the same kernel; a probe goes to the key's owner over NVLink after the local filter
+// said "maybe", a claim to the owner of the read's range of the bitmap, the candidate read comes from the local replica.
 //
 // Not in the reference (switchable, params.extend): a new chain is first extended to the LEFT of its head by walking the
 // reverse-complement strand, and that run is written in front of the head in reverse order.  The streams only encode
