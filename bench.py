@@ -710,6 +710,48 @@ def run_one_job(args, rank, world, local, dist, json_fd):
                 one_gpu = {"error": str(ex)[:300]}
         dist.barrier()
 
+    # ---- secondary figure: the other split, one INDEPENDENT configs[1] read set per GPU (weak scaling, no data-path
+    # collective), a few steps on a context of its own
+    read_sets = None
+    if args.read_sets_steps > 0:
+        try:
+            c1cfg = dict(W.CONFIGS[1])
+            w1 = W.make(c1cfg["reads"], c1cfg["L"], c1cfg["genome"], rc=c1cfg["rc"], errors=c1cfg["errors"], seed=args.seed + 7919 * rank,
+                        threads=thr, keep_all=False)
+            dC1 = torch.empty(w1["clean"].size + 16, dtype=torch.uint8, device="cuda")
+            dC1[: w1["clean"].size].copy_(torch.from_numpy(w1["clean"]))
+            dN1 = torch.empty(w1["withN"].size + 16, dtype=torch.uint8, device="cuda")
+            dN1[: w1["withN"].size].copy_(torch.from_numpy(w1["withN"]))
+            c2 = harc_b200.HarcGpu(c1cfg["L"], device=local, walkers=args.walkers, file_sets=1, reads_per_walker=args.reads_per_walker, extend=args.extend)
+            st2 = torch.cuda.ExternalStream(c2.stream())
+
+            def rs_step():
+                c2.load_reads_device(dC1.data_ptr(), w1["n_clean"])
+                c2.build_dicts()
+                c2.reorder()
+                c2.load_pool_device(dN1.data_ptr(), w1["n_N"])
+                c2.encode()
+            for _ in range(3):
+                rs_step()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st2)
+            for _ in range(args.read_sets_steps):
+                rs_step()
+            e1.record(st2)
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / args.read_sets_steps], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rs_ms = float(t.item())
+            read_sets = {"value": world * c1cfg["reads"] / rs_ms / 1e3, "unit": "Mreads/s", "ms_per_step": rs_ms, "steps": args.read_sets_steps,
+                         "scaling": "weak", "what": "one independent configs[1] read set (35 M reads) per GPU, no data-path collective; "
+                                                    "reads of all ranks / slowest rank, device-timed"}
+            c2.close()
+            del dC1, dN1, w1
+        except Exception as ex:
+            read_sets = {"error": str(ex)[:300]}
+        dist.barrier()
+
     value = total_reads / (ms_dev / 1000.0) / 1e6
     e2e = total_reads / (ms_e2e / 1000.0) / 1e6
     if rank == 0:
@@ -741,7 +783,7 @@ def run_one_job(args, rank, world, local, dist, json_fd):
                                        "walk_kernel<%d, %d>, per GPU" % (ctx.NW(), args.lanes or 32)),
             "e2e": {"value": e2e, "unit": "Mreads/s", "ms_per_step": ms_e2e, "what": "one job at a time; every rank uploads its slice from pinned host "
                     "memory and reads back its file set", "h2d_bytes_per_step": int(h_clean.numel() + h_N.numel()) * world, "d2h_bytes_per_step": int(last.get("d2h", 0)) * world},
-            "exchange_bytes_per_step": comm_bytes, "verify": verify, "one_gpu_same_workload": one_gpu,
+            "exchange_bytes_per_step": comm_bytes, "verify": verify, "one_gpu_same_workload": one_gpu, "read_sets": read_sets,
             "scaling_note": "strong scaling of ONE %d-read job; `bench.py --gpus 1` runs configs[1] (the metric's configuration, a different "
                             "workload), so the one-GPU time of THIS workload is measured here, on rank 0's GPU in the same run "
                             "(one_gpu_same_workload)" % total_reads, "laps_ms_rank0": laps or None, "detail": detail,
@@ -775,6 +817,8 @@ def main():
                     help="N>1: one-job = ONE read set on all ranks (strong scaling, default); read-sets = every rank compresses its own "
                          "read set (weak scaling, no data-path collective)")
     ap.add_argument("--shard-dicts", type=int, default=1, help="one-job mode: 1 = dictionaries sharded by key over the GPUs, 0 = replicated")
+    ap.add_argument("--read-sets-steps", type=int, default=5,
+                    help="one-job mode: timed steps of the secondary read-sets figure (one independent configs[1] set per GPU); 0 = skip")
     ap.add_argument("--t1", type=int, default=1, help="one-job mode: also time the whole workload on rank 0's GPU alone (outside the timed region)")
     ap.add_argument("--pipeline", type=int, default=3, help="e2e: jobs in flight (contexts) for the pipelined figure; 1 = off")
     ap.add_argument("--ref-budget-s", type=float, default=600.0, help="--impl reference: wall-time bound of the whole run")

@@ -5,7 +5,7 @@ O=gpurun_out
 N=${1:-8}
 free -g | head -2; nproc
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-HARCGPU_JOB_TIMEOUT_S=120 timeout 1700 $TR bench.py --gpus $N --config 4 --steps 3 --warmup 2 --no-e2e --t1 0 > $O/s17_c4_n$N.json 2> $O/s17_c4_n$N.err; echo "rc=$?"
+HARCGPU_JOB_TIMEOUT_S=120 timeout 1700 $TR bench.py --gpus $N --config 4 --steps 3 --warmup 2 --no-e2e --t1 0 --read-sets-steps 0 > $O/s17_c4_n$N.json 2> $O/s17_c4_n$N.err; echo "rc=$?"
 python - <<P
 import json
 try:
