@@ -1,10 +1,9 @@
 #!/bin/bash
-# one GPU, final build: repeat-rich shape with laps, whole GPU test suite, the default bench line, ncu capture of the walk
+# one GPU, final build: whole GPU test suite, the default bench line, (optionally) the ncu capture of the walk
 cd "$(dirname "$0")/.."
 O=gpurun_out
-HARCGPU_LAPS=1 timeout 300 python tools/run_shape.py 3e6 100 repeats:20 1 1 > $O/f1_rep.txt 2> $O/f1_rep.err; echo "rep rc=$?"; cat $O/f1_rep.txt
 timeout 1200 python -m pytest tests -m gpu -x -q > $O/f1_pytest.log 2>&1; echo "pytest rc=$?" >> $O/f1_pytest.log; tail -4 $O/f1_pytest.log
-timeout 1200 python bench.py > $O/f1_bench.json 2> $O/f1_bench.err; echo "bench rc=$?"
+timeout 1200 python bench.py --steps 20 --warmup 5 > $O/f1_bench.json 2> $O/f1_bench.err; echo "bench rc=$?"
 python - <<P
 import json
 try:
@@ -15,4 +14,6 @@ try:
 except Exception as e:
     print("ERR", e); print(open("$O/f1_bench.err").read()[-1500:])
 P
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:walk_kernel -c 1 -o $O/f1_walk -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --ingest-reads 0 > $O/f1_w.log 2>&1; echo "walk capture rc=$?"
+if [ "$1" = "ncu" ]; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:walk_kernel -c 1 -o $O/f1_walk -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --ingest-reads 0 > $O/f1_w.log 2>&1; echo "walk capture rc=$?"
+fi
