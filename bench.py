@@ -506,7 +506,11 @@ def run_single(args, rank, world, local, dist, json_fd):
     if ingest:
         out["ingest"] = ingest
     # ---- reference on the same workload (full size, one step) + bits/base of both
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and cfg["reads"] * L > 6e9 and not args.force_cpu_baseline:
+        # the reference needs ~10 s per Gbase on 16 threads: the default bench run stays within minutes
+        out["cpu_baseline"] = {"skipped": "%d reads x %d bp would take the reference several minutes to hours; run with --force-cpu-baseline "
+                                          "or `--impl reference --config %d`" % (cfg["reads"], L, cfg["index"])}
+    elif not args.no_cpu_baseline and world == 1:
         try:
             import refrun as R
             T = reference_threads(L)
@@ -823,6 +827,7 @@ def main():
     ap.add_argument("--pipeline", type=int, default=3, help="e2e: jobs in flight (contexts) for the pipelined figure; 1 = off")
     ap.add_argument("--ref-budget-s", type=float, default=600.0, help="--impl reference: wall-time bound of the whole run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--force-cpu-baseline", action="store_true", help="run the reference on the host even for the large configs")
     ap.add_argument("--no-bits", action="store_true", help="skip the bits/base block (stage III stand-in over both archives)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer pass")
     ap.add_argument("--ingest-reads", type=float, default=8e6,
